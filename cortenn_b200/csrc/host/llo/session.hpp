@@ -1,0 +1,34 @@
+///
+/// session.hpp
+/// llo
+///
+/// Purpose:
+/// Process-wide evaluator options.  The reference has no runtime flags
+/// (SURVEY.md 5); these only select between mechanisms that give the same
+/// results within the stated tolerances.
+///
+///   "plan"        1 = lower graphs through the planner (views, constant
+///                 folding, fused elementwise programs, GEMM lowering);
+///                 0 = one C-ABI operator call per functor
+///   "simplify"    1 = allow x*1 -> x and (x*y)/x -> y in derived graphs
+///                 (the second is inexact by <= 1 ulp and defined at x == 0,
+///                 where the reference yields NaN)
+///   "tf32x3"      1 = opt-in 3xTF32 tensor-core GEMM for fp32
+///   "sequential_reduce" 1 = reference summation order for reductions
+///
+
+#ifndef LLO_SESSION_HPP
+#define LLO_SESSION_HPP
+
+#include <string>
+
+namespace llo
+{
+
+void set_option (std::string name, long value);
+
+long get_option (std::string name);
+
+}
+
+#endif // LLO_SESSION_HPP

@@ -1,0 +1,299 @@
+#include <cstdlib>
+#include <mutex>
+
+#include "llo/data.hpp"
+
+#ifdef LLO_DATA_HPP
+
+namespace llo
+{
+
+namespace device
+{
+
+static llo_cuda_ctx* global_ctx = nullptr;
+
+static std::string init_error;
+
+static std::once_flag init_once;
+
+static void init_ctx (void)
+{
+	int dev = 0;
+	if (const char* env = std::getenv("LLO_CUDA_DEVICE"))
+	{
+		dev = std::atoi(env);
+	}
+	else if (const char* env = std::getenv("LOCAL_RANK"))
+	{
+		dev = std::atoi(env);
+	}
+	if (LLO_OK != llo_cuda_init(dev, &global_ctx))
+	{
+		global_ctx = nullptr;
+		init_error = llo_cuda_last_error();
+	}
+}
+
+llo_cuda_ctx* ctx (void)
+{
+	std::call_once(init_once, init_ctx);
+	if (nullptr == global_ctx)
+	{
+		logs::fatalf("llo CUDA context unavailable (%s): the B200 evaluator "
+			"has no CPU fallback", init_error.c_str());
+	}
+	return global_ctx;
+}
+
+bool available (void)
+{
+	std::call_once(init_once, init_ctx);
+	return nullptr != global_ctx;
+}
+
+void check (int status)
+{
+	if (LLO_OK == status)
+	{
+		return;
+	}
+	if (LLO_ERR_UNSUPPORTED_TYPED_OP == status)
+	{
+		throw std::bad_function_call();
+	}
+	logs::fatal(llo_cuda_last_error());
+}
+
+std::shared_ptr<char> alloc (size_t nbytes)
+{
+	llo_cuda_ctx* c = ctx();
+	void* ptr = nullptr;
+	check(llo_cuda_alloc(c, nbytes, &ptr));
+	return std::shared_ptr<char>((char*) ptr,
+		[c](char* p) { llo_cuda_free(c, p); });
+}
+
+static const size_t pin_threshold = 1 << 16;
+
+std::shared_ptr<char> host_alloc (size_t nbytes)
+{
+	if (nbytes >= pin_threshold && available())
+	{
+		llo_cuda_ctx* c = ctx();
+		void* ptr = nullptr;
+		if (LLO_OK == llo_cuda_host_alloc(c, nbytes, &ptr))
+		{
+			return std::shared_ptr<char>((char*) ptr,
+				[c](char* p) { llo_cuda_host_free(c, p); });
+		}
+	}
+	return std::shared_ptr<char>((char*) std::malloc(std::max<size_t>(nbytes, 1)),
+		[](char* p) { std::free(p); });
+}
+
+}
+
+GenericData::GenericData (ade::Shape shape, age::_GENERATED_DTYPE dtype) :
+	shape_(shape), dtype_(dtype),
+	device_(device::alloc(shape.n_elems() * age::type_size(dtype))) {}
+
+void GenericData::copyover (const char* indata, age::_GENERATED_DTYPE intype)
+{
+	llo_cuda_ctx* c = device::ctx();
+	size_t n = shape_.n_elems();
+	if (dtype_ == intype)
+	{
+		device::check(llo_cuda_h2d(c, device_.get(), indata, nbytes()));
+	}
+	else
+	{
+		size_t inbytes = n * age::type_size(intype);
+		std::shared_ptr<char> staged = device::alloc(inbytes);
+		device::check(llo_cuda_h2d(c, staged.get(), indata, inbytes));
+		device::check(llo_cuda_convert(c, device_.get(), dtype_,
+			staged.get(), intype, n));
+	}
+	data_ = nullptr;
+}
+
+char* GenericData::fetch (void)
+{
+	if (nullptr == data_ && nullptr != device_)
+	{
+		data_ = device::host_alloc(nbytes());
+		device::check(llo_cuda_d2h(device::ctx(),
+			data_.get(), device_.get(), nbytes()));
+	}
+	return data_.get();
+}
+
+Variable::Variable (const char* data, age::_GENERATED_DTYPE dtype,
+	ade::Shape shape, std::string label) :
+	label_(label), shape_(shape), dtype_(dtype)
+{
+	if (nullptr != data)
+	{
+		host_ = device::host_alloc(nbytes());
+		std::memcpy(host_.get(), data, nbytes());
+	}
+	else
+	{
+		// zeros (llo/data.hpp:72-79), kept lazy
+		fill_.assign(age::type_size(dtype), 0);
+	}
+}
+
+Variable* Variable::filled (const char* elem, age::_GENERATED_DTYPE dtype,
+	ade::Shape shape, std::string label)
+{
+	Variable* out = new Variable(nullptr, dtype, shape, label);
+	out->fill_.assign(elem, elem + age::type_size(dtype));
+	return out;
+}
+
+Variable::Variable (const Variable& other) :
+	label_(other.label_), fill_(other.fill_),
+	shape_(other.shape_), dtype_(other.dtype_)
+{
+	if (nullptr != other.host_)
+	{
+		host_ = device::host_alloc(nbytes());
+		std::memcpy(host_.get(), other.host_.get(), nbytes());
+	}
+}
+
+Variable& Variable::operator = (const Variable& other)
+{
+	if (this != &other)
+	{
+		label_ = other.label_;
+		fill_ = other.fill_;
+		shape_ = other.shape_;
+		dtype_ = other.dtype_;
+		host_ = nullptr;
+		if (nullptr != other.host_)
+		{
+			host_ = device::host_alloc(nbytes());
+			std::memcpy(host_.get(), other.host_.get(), nbytes());
+		}
+		++version_;
+		mirrors_.clear();
+	}
+	return *this;
+}
+
+Variable& Variable::operator = (GenericRef data)
+{
+	if (false == data.shape_.compatible_after(shape(), 0))
+	{
+		logs::fatalf("cannot assign data of incompatible shaped %s to "
+			"internal data of shape %s", data.shape_.to_string().c_str(),
+			shape().to_string().c_str());
+	}
+	if (data.dtype_ != dtype_)
+	{
+		logs::fatalf("cannot assign data of incompatible types %s "
+			"(external) and %s (internal)",
+			age::name_type(data.dtype_).c_str(), age::name_type(dtype_).c_str());
+	}
+	if (nullptr == host_)
+	{
+		host_ = device::host_alloc(nbytes());
+	}
+	fill_.clear();
+	std::memcpy(host_.get(), data.data_, nbytes());
+	++version_;
+	return *this;
+}
+
+void Variable::materialize (void) const
+{
+	if (nullptr != host_)
+	{
+		return;
+	}
+	size_t esize = age::type_size(dtype_);
+	size_t n = shape_.n_elems();
+	host_ = device::host_alloc(nbytes());
+	char* dst = host_.get();
+	bool allzero = std::all_of(fill_.begin(), fill_.end(),
+		[](char c) { return 0 == c; });
+	if (allzero)
+	{
+		std::memset(dst, 0, n * esize);
+		return;
+	}
+	for (size_t i = 0; i < n; ++i)
+	{
+		std::memcpy(dst + i * esize, fill_.data(), esize);
+	}
+}
+
+double Variable::fill_value (void) const
+{
+	if (fill_.empty())
+	{
+		logs::fatal("cannot get fill value of a non-constant variable");
+	}
+	const char* p = fill_.data();
+	switch (dtype_)
+	{
+#define AGE_X(NAME, CTYPE) case age::NAME:\
+		{ CTYPE v; std::memcpy(&v, p, sizeof(CTYPE)); return (double) v; }
+		AGE_DTYPES(AGE_X)
+#undef AGE_X
+		default: break;
+	}
+	logs::fatal("cannot get fill value of bad type");
+}
+
+std::shared_ptr<char> Variable::device_data (
+	age::_GENERATED_DTYPE dtype) const
+{
+	for (Mirror& m : mirrors_)
+	{
+		if (m.dtype_ == dtype)
+		{
+			if (m.version_ == version_)
+			{
+				return m.data_;
+			}
+			break;
+		}
+	}
+	llo_cuda_ctx* c = device::ctx();
+	size_t n = shape_.n_elems();
+
+	// raw mirror in the leaf's own type first
+	std::shared_ptr<char> raw;
+	for (Mirror& m : mirrors_)
+	{
+		if (m.dtype_ == dtype_ && m.version_ == version_)
+		{
+			raw = m.data_;
+		}
+	}
+	if (nullptr == raw)
+	{
+		raw = device::alloc(nbytes());
+		device::check(llo_cuda_h2d(c, raw.get(), data(), nbytes()));
+		mirrors_.erase(std::remove_if(mirrors_.begin(), mirrors_.end(),
+			[&](Mirror& m) { return m.dtype_ == dtype_; }), mirrors_.end());
+		mirrors_.push_back(Mirror{dtype_, version_, raw});
+	}
+	if (dtype == dtype_)
+	{
+		return raw;
+	}
+	std::shared_ptr<char> conv = device::alloc(n * age::type_size(dtype));
+	device::check(llo_cuda_convert(c, conv.get(), dtype, raw.get(), dtype_, n));
+	mirrors_.erase(std::remove_if(mirrors_.begin(), mirrors_.end(),
+		[&](Mirror& m) { return m.dtype_ == dtype; }), mirrors_.end());
+	mirrors_.push_back(Mirror{dtype, version_, conv});
+	return conv;
+}
+
+}
+
+#endif

@@ -1,0 +1,354 @@
+///
+/// module.cpp
+///
+/// Python surface of the evaluator, kept identical to the reference's two
+/// pybind modules:
+///   `age`  — one graph builder per op-table entry, the second overload of a
+///            name gets the suffix 0 (reduce_sum / reduce_sum0 ...), class
+///            Tensor                      (pybinder/pyapi_plugin.py:19-54)
+///   `llo`  — variable, Variable.assign, evaluate, derive, seed, print_graph,
+///            Tensor.__str__/shape()/children()   (llo/python/llo.cpp:156-215)
+/// numpy shapes are the reverse of ade shapes (llo/python/llo.cpp:18-34).
+///
+/// Additions: evaluate() honours the exact numpy dtype
+/// (the reference only distinguishes 'f' -> DOUBLE and 'i' -> INT64, which
+/// the float64 / int64 defaults still select), unsigned dtypes are accepted,
+/// and evaluate_device() leaves the result in HBM.
+///
+
+#include "pybind11/pybind11.h"
+#include "pybind11/numpy.h"
+#include "pybind11/stl.h"
+
+#include "llo/llo.hpp"
+#include "llo/session.hpp"
+
+#include "dbg/ade.hpp"
+
+namespace py = pybind11;
+
+namespace pyllo
+{
+
+static ade::Shape p2cshape (const std::vector<py::ssize_t>& pyshape)
+{
+	return ade::Shape(std::vector<ade::DimT>(
+		pyshape.rbegin(), pyshape.rend()));
+}
+
+static std::vector<py::ssize_t> c2pshape (const ade::Shape& cshape)
+{
+	auto it = cshape.begin();
+	auto et = cshape.end();
+	while (it != et && *(et - 1) == 1)
+	{
+		--et;
+	}
+	std::vector<py::ssize_t> fwd(it, et);
+	return std::vector<py::ssize_t>(fwd.rbegin(), fwd.rend());
+}
+
+static age::_GENERATED_DTYPE exact_dtype (py::dtype dtype, const char* what)
+{
+	char kind = dtype.kind();
+	py::ssize_t tbytes = dtype.itemsize();
+	switch (kind)
+	{
+		case 'f':
+			switch (tbytes)
+			{
+				case 4: return age::FLOAT;
+				case 8: return age::DOUBLE;
+				default:
+					logs::fatalf("unsupported float type with %d bytes",
+						(int) tbytes);
+			}
+		case 'i':
+			switch (tbytes)
+			{
+				case 1: return age::INT8;
+				case 2: return age::INT16;
+				case 4: return age::INT32;
+				case 8: return age::INT64;
+				default:
+					logs::fatalf("unsupported integer type with %d bytes",
+						(int) tbytes);
+			}
+		case 'u':
+			switch (tbytes)
+			{
+				case 1: return age::UINT8;
+				case 2: return age::UINT16;
+				case 4: return age::UINT32;
+				case 8: return age::UINT64;
+				default:
+					logs::fatalf("unsupported integer type with %d bytes",
+						(int) tbytes);
+			}
+		default:
+			logs::fatalf("unknown dtype %c", kind);
+	}
+	(void) what;
+	return age::BAD_TYPE;
+}
+
+static llo::VarptrT variable (py::array data, std::string label)
+{
+	py::array dense = py::array::ensure(data, py::array::c_style);
+	py::buffer_info info = dense.request();
+	ade::Shape shape = p2cshape(info.shape);
+	age::_GENERATED_DTYPE dtype = exact_dtype(dense.dtype(), "variable");
+	if ((size_t) info.size != shape.n_elems())
+	{
+		logs::fatalf("cannot create variable with data size %d "
+			"against shape %s", (int) info.size, shape.to_string().c_str());
+	}
+	return llo::VarptrT(new llo::Variable(
+		(const char*) info.ptr, dtype, shape, label));
+}
+
+// reference: llo/python/llo.cpp:101-124 reads every 'f' array as double and
+// every 'i' array as int64; here the array is cast to the variable's own
+// type first, which is the same thing whenever the reference's read is valid
+static void assign (llo::Variable* target, py::array data)
+{
+	age::_GENERATED_DTYPE want =
+		(age::_GENERATED_DTYPE) target->type_code();
+	age::_GENERATED_DTYPE have = exact_dtype(data.dtype(), "assign");
+	py::array dense = py::array::ensure(data, py::array::c_style);
+	py::buffer_info info = dense.request();
+	ade::Shape shape = p2cshape(info.shape);
+	if (have != want)
+	{
+		logs::fatalf("cannot assign data of incompatible types %s "
+			"(external) and %s (internal)",
+			age::name_type(have).c_str(), age::name_type(want).c_str());
+	}
+	*target = llo::GenericRef((char*) info.ptr, shape, want);
+}
+
+static age::_GENERATED_DTYPE eval_dtype (py::dtype dtype)
+{
+	return exact_dtype(dtype, "evaluate");
+}
+
+static py::array evaluate (ade::TensptrT tens, py::dtype dtype)
+{
+	age::_GENERATED_DTYPE ctype = eval_dtype(dtype);
+	llo::GenericData gdata;
+	{
+		py::gil_scoped_release release;
+		gdata = llo::eval(tens, ctype);
+	}
+	auto pshape = c2pshape(gdata.shape_);
+	// no base object: numpy copies the buffer (as in the reference)
+	return py::array(dtype, pshape, gdata.data_.get());
+}
+
+/// Device-resident result handle
+struct DeviceResult
+{
+	llo::GenericData data_;
+};
+
+}
+
+PYBIND11_MODULE(_C, m)
+{
+	m.doc() = "cortenn_b200: B200-native llo evaluator";
+
+	py::module_ age_m = m.def_submodule("age", "pybind ade generator");
+	py::module_ llo_m = m.def_submodule("llo", "llo variables");
+
+	py::class_<ade::iTensor,ade::TensptrT> tensor(age_m, "Tensor");
+	tensor
+		.def("__str__", &ade::iTensor::to_string)
+		.def("shape", [](ade::TensptrT self)
+		{
+			auto pshape = pyllo::c2pshape(self->shape());
+			std::vector<int> ipshape(pshape.begin(), pshape.end());
+			return py::array(ipshape.size(), ipshape.data());
+		})
+		.def("children", [](ade::TensptrT self)
+		{
+			std::vector<ade::TensptrT> tens;
+			if (auto f = dynamic_cast<ade::iFunctor*>(self.get()))
+			{
+				for (const ade::MappedTensor& arg : f->get_children())
+				{
+					tens.push_back(arg.get_tensor());
+				}
+			}
+			return tens;
+		})
+		.def("opname", [](ade::TensptrT self) -> std::string
+		{
+			if (auto f = dynamic_cast<ade::iFunctor*>(self.get()))
+			{
+				return f->get_opcode().name_;
+			}
+			return "";
+		});
+
+	py::class_<llo::Variable,ade::iTensor,llo::VarptrT> variable(
+		llo_m, "Variable");
+	variable
+		.def("assign", [](llo::VarptrT self, py::array data)
+		{
+			pyllo::assign(self.get(), data);
+		}, "assign to variable")
+		.def_readwrite("label", &llo::Variable::label_);
+
+	// ---- age: graph builders (llo/cfg/llo.json:125-531) ----
+	using T = ade::TensptrT;
+#define AGE_UNARY(NAME) age_m.def(#NAME, [](T a) { return age::NAME(a); },\
+	"ade::TensptrT " #NAME " (ade::TensptrT arg1)");
+	AGE_UNARY(abs) AGE_UNARY(neg) AGE_UNARY(sin) AGE_UNARY(cos) AGE_UNARY(tan)
+	AGE_UNARY(exp) AGE_UNARY(log) AGE_UNARY(sqrt) AGE_UNARY(round)
+#undef AGE_UNARY
+	age_m.def("flip", [](T a, uint8_t dim) { return age::flip(a, dim); });
+#define AGE_BINARY(NAME) age_m.def(#NAME, [](T a, T b) { return age::NAME(a, b); },\
+	"ade::TensptrT " #NAME " (ade::TensptrT arg1, ade::TensptrT arg2)");
+	AGE_BINARY(pow) AGE_BINARY(add) AGE_BINARY(sub) AGE_BINARY(mul)
+	AGE_BINARY(div) AGE_BINARY(eq) AGE_BINARY(neq) AGE_BINARY(lt) AGE_BINARY(gt)
+	AGE_BINARY(rand_bino) AGE_BINARY(rand_unif) AGE_BINARY(rand_norm)
+#undef AGE_BINARY
+	age_m.def("n_elems", [](T a) { return age::n_elems(a); });
+	age_m.def("n_dims", [](T a, uint8_t rank) { return age::n_dims(a, rank); });
+#define AGE_NARY(NAME) age_m.def(#NAME, [](ade::TensT a) { return age::NAME(a); });
+	AGE_NARY(sum) AGE_NARY(prod) AGE_NARY(min) AGE_NARY(max)
+#undef AGE_NARY
+#define AGE_REDUCE(NAME)\
+	age_m.def(#NAME, [](T a, uint8_t dim) { return age::NAME(a, dim); });\
+	age_m.def(#NAME "0", [](T a) { return age::NAME(a); });
+	AGE_REDUCE(reduce_sum) AGE_REDUCE(reduce_prod)
+	AGE_REDUCE(reduce_min) AGE_REDUCE(reduce_max)
+#undef AGE_REDUCE
+	age_m.def("permute", [](T a, std::vector<uint8_t> order)
+		{ return age::permute(a, order); });
+	age_m.def("extend", [](T a, uint8_t rank, std::vector<ade::DimT> ext)
+		{ return age::extend(a, rank, ext); });
+	age_m.def("transpose", [](T a) { return age::transpose(a); });
+	age_m.def("reduce_mean", [](T a) { return age::reduce_mean(a); });
+	age_m.def("matmul", [](T a, T b) { return age::matmul(a, b); });
+	age_m.def("convolution", [](T a, T b) { return age::convolution(a, b); });
+
+	// raw functor construction with explicit 9x9 maps, for tests that
+	// exercise arbitrary CoordMaps (llo/test/test_operator.cpp:29-38)
+	age_m.def("functor", [](std::string opname, std::vector<T> args,
+		std::vector<py::array_t<double>> shapers,
+		std::vector<py::array_t<double>> coorders,
+		std::vector<bool> pushes)
+	{
+		age::_GENERATED_OPCODE code = age::get_op(opname);
+		if (age::BAD_OP == code)
+		{
+			logs::fatalf("unknown opcode %s", opname.c_str());
+		}
+		auto to_map = [](py::array_t<double>& mat) -> ade::CoordptrT
+		{
+			auto r = mat.unchecked<2>();
+			if (r.shape(0) != ade::mat_dim || r.shape(1) != ade::mat_dim)
+			{
+				logs::fatal("coordinate maps are 9x9");
+			}
+			return std::make_shared<ade::CoordMap>([&](ade::MatrixT m)
+			{
+				for (int i = 0; i < ade::mat_dim; ++i)
+				{
+					for (int j = 0; j < ade::mat_dim; ++j)
+					{
+						m[i][j] = r(i, j);
+					}
+				}
+			});
+		};
+		ade::ArgsT margs;
+		for (size_t i = 0; i < args.size(); ++i)
+		{
+			margs.push_back(ade::MappedTensor(args[i], to_map(shapers[i]),
+				pushes[i], to_map(coorders[i])));
+		}
+		return T(ade::Functor::get(
+			ade::Opcode{opname, (size_t) code}, margs));
+	});
+	// functor over extend-mapped arguments (llo/test/test_api.cpp:1024-1027)
+	age_m.def("functor_extended", [](std::string opname, std::vector<T> args,
+		uint8_t rank, std::vector<ade::DimT> ext)
+	{
+		age::_GENERATED_OPCODE code = age::get_op(opname);
+		ade::ArgsT margs;
+		for (T& a : args)
+		{
+			margs.push_back(ade::extend_map(a, rank, ext));
+		}
+		return T(ade::Functor::get(
+			ade::Opcode{opname, (size_t) code}, margs));
+	});
+
+	// ---- llo ----
+	llo_m.def("variable", &pyllo::variable, "create tensor variable",
+		py::arg("data"), py::arg("label") = "");
+	llo_m.def("scalar", [](double value, std::vector<py::ssize_t> shape,
+		std::string label)
+	{
+		return llo::get_scalar<double>(value, pyllo::p2cshape(shape), label);
+	}, py::arg("value"), py::arg("shape"), py::arg("label") = "");
+	llo_m.def("evaluate", &pyllo::evaluate,
+		"evaluate data of tens according to dtype",
+		py::arg("tens"), py::arg("dtype") = py::dtype::of<double>());
+	llo_m.def("derive", [](T root, T target)
+		{ return llo::derive(root, target.get()); },
+		"derive tensor with respect to some derive");
+	llo_m.def("seed", [](size_t seed)
+		{
+			llo::device::check(llo_cuda_seed(llo::device::ctx(), seed));
+		}, "seed internal rng");
+	llo_m.def("print_graph", [](T root, bool showshape)
+		{
+			PrettyEquation peq;
+			peq.showshape_ = showshape;
+			std::stringstream ss;
+			peq.print(ss, root);
+			py::print(ss.str(), py::arg("end") = "");
+		}, "print graph of root tensor",
+		py::arg("root"), py::arg("showshape") = false);
+	llo_m.def("graph_string", [](T root, bool showshape)
+		{
+			PrettyEquation peq;
+			peq.showshape_ = showshape;
+			std::stringstream ss;
+			peq.print(ss, root);
+			return ss.str();
+		}, py::arg("root"), py::arg("showshape") = false);
+
+	// ---- device-resident additions ----
+	py::class_<pyllo::DeviceResult>(llo_m, "DeviceResult")
+		.def("ptr", [](pyllo::DeviceResult& self)
+			{ return (uintptr_t) self.data_.device_.get(); })
+		.def("nbytes", [](pyllo::DeviceResult& self)
+			{ return self.data_.nbytes(); })
+		.def("shape", [](pyllo::DeviceResult& self)
+			{ return pyllo::c2pshape(self.data_.shape_); })
+		.def("numpy", [](pyllo::DeviceResult& self, py::dtype dtype)
+			{
+				auto pshape = pyllo::c2pshape(self.data_.shape_);
+				return py::array(dtype, pshape, self.data_.fetch());
+			});
+	llo_m.def("evaluate_device", [](T tens, py::dtype dtype)
+		{
+			pyllo::DeviceResult out;
+			py::gil_scoped_release release;
+			out.data_ = llo::eval_device(tens, pyllo::eval_dtype(dtype));
+			return out;
+		}, py::arg("tens"), py::arg("dtype") = py::dtype::of<double>());
+	llo_m.def("available", []() { return llo::device::available(); });
+	llo_m.def("sync", []()
+		{ llo::device::check(llo_cuda_sync(llo::device::ctx())); });
+	llo_m.def("launch_count", []()
+		{ return llo_cuda_launch_count(llo::device::ctx()); });
+	llo_m.def("context", []()
+		{ return (uintptr_t) llo::device::ctx(); });
+	llo_m.def("set_option", &llo::set_option);
+	llo_m.def("get_option", &llo::get_option);
+}
