@@ -91,6 +91,8 @@ def build_cuda(verbose=False, jobs=None):
     os.makedirs(objdir, exist_ok=True)
     sources = sorted(f for f in os.listdir(src_dir) if f.endswith(".cu"))
     headers = _headers(src_dir, INCLUDE)
+    if not verbose and not _stale(cuda_lib_path(), [os.path.join(src_dir, f) for f in sources] + headers):
+        return ""  # prebuilt library is current (e.g. on the GPU box)
     todo = []
     objs = []
     for name in sources:
@@ -125,6 +127,8 @@ def build_host():
                if f.endswith(".cpp")]
     sources.append(os.path.join(CSRC, "pybind", "module.cpp"))
     headers = _headers(host, INCLUDE)
+    if not _stale(host_lib_path(), sources + headers + [cuda_lib_path()]):
+        return
     incs = ["-I", host, "-I", INCLUDE]
     for inc in pybind_includes():
         incs += ["-I", inc]

@@ -73,6 +73,10 @@ EXPORTS = {
     "llo_cuda_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
     "llo_cuda_sync": (C.c_int, [C.c_void_p]),
     "llo_cuda_launch_count": (C.c_uint64, [C.c_void_p]),
+    "llo_cuda_event_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "llo_cuda_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "llo_cuda_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
+    "llo_cuda_event_destroy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "llo_cuda_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint64]),
     "llo_cuda_unary": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(Arg)]),
     "llo_cuda_binary": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(Arg), C.POINTER(Arg)]),
@@ -148,16 +152,22 @@ def make_arg(ptr, shape, coorder=None, push=False):
 class Context:
     """One llo_cuda_ctx plus small numpy <-> device helpers."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, handle=None):
+        """handle: adopt an existing llo_cuda_ctx* (e.g. the evaluator's,
+        from cortenn_b200.llo.context()) instead of creating one"""
         self.lib = lib()
-        handle = C.c_void_p()
-        check(self.lib.llo_cuda_init(device, C.byref(handle)))
+        self.owned = handle is None
+        if handle is None:
+            handle = C.c_void_p()
+            check(self.lib.llo_cuda_init(device, C.byref(handle)))
+        else:
+            handle = C.c_void_p(handle)
         self.handle = handle
 
     def close(self):
-        if self.handle:
+        if self.handle and self.owned:
             self.lib.llo_cuda_destroy(self.handle)
-            self.handle = None
+        self.handle = None
 
     def alloc(self, nbytes):
         ptr = C.c_void_p()
@@ -183,6 +193,19 @@ class Context:
 
     def launch_count(self):
         return self.lib.llo_cuda_launch_count(self.handle)
+
+    def event(self):
+        ev = C.c_void_p()
+        check(self.lib.llo_cuda_event_create(self.handle, C.byref(ev)))
+        return ev
+
+    def record(self, ev):
+        check(self.lib.llo_cuda_event_record(self.handle, ev))
+
+    def elapsed_ms(self, start, stop):
+        ms = C.c_float()
+        check(self.lib.llo_cuda_event_elapsed_ms(self.handle, start, stop, C.byref(ms)))
+        return ms.value
 
     def op_exec(self, opcode, np_dtype, out_ptr, outshape, args):
         arr = (Arg * len(args))(*args)

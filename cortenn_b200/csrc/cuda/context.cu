@@ -256,6 +256,34 @@ uint64_t llo_cuda_launch_count (llo_cuda_ctx* ctx)
 	return ctx->launches;
 }
 
+int llo_cuda_event_create (llo_cuda_ctx* ctx, void** event)
+{
+	cudaEvent_t ev;
+	LLO_CUDA_TRY(cudaSetDevice(ctx->device));
+	LLO_CUDA_TRY(cudaEventCreate(&ev));
+	*event = (void*) ev;
+	return LLO_OK;
+}
+
+int llo_cuda_event_record (llo_cuda_ctx* ctx, void* event)
+{
+	LLO_CUDA_TRY(cudaEventRecord((cudaEvent_t) event, ctx->stream));
+	return LLO_OK;
+}
+
+int llo_cuda_event_elapsed_ms (llo_cuda_ctx*, void* start, void* stop, float* ms)
+{
+	LLO_CUDA_TRY(cudaEventSynchronize((cudaEvent_t) stop));
+	LLO_CUDA_TRY(cudaEventElapsedTime(ms, (cudaEvent_t) start, (cudaEvent_t) stop));
+	return LLO_OK;
+}
+
+int llo_cuda_event_destroy (llo_cuda_ctx*, void* event)
+{
+	LLO_CUDA_TRY(cudaEventDestroy((cudaEvent_t) event));
+	return LLO_OK;
+}
+
 int llo_cuda_seed (llo_cuda_ctx* ctx, uint64_t seed)
 {
 	ctx->seed = seed;

@@ -95,6 +95,11 @@ int llo_cuda_memset (llo_cuda_ctx* ctx, void* dst, int byte, size_t bytes);
 int llo_cuda_sync (llo_cuda_ctx* ctx);
 /* number of kernels this context has launched so far (bench `gpu_launches`) */
 uint64_t llo_cuda_launch_count (llo_cuda_ctx* ctx);
+/* CUDA events on the context's stream, for device-side timing */
+int llo_cuda_event_create (llo_cuda_ctx* ctx, void** event);
+int llo_cuda_event_record (llo_cuda_ctx* ctx, void* event);
+int llo_cuda_event_elapsed_ms (llo_cuda_ctx* ctx, void* start, void* stop, float* ms);
+int llo_cuda_event_destroy (llo_cuda_ctx* ctx, void* event);
 
 /* ---- K0: leaf dtype conversion, GenericData::copyover
  *      (llo/src/data.cpp:20-72) ---- */

@@ -1,0 +1,53 @@
+"""CPU: the C-ABI library loads and exports every symbol include/llo_cuda.h
+declares (no compute calls without a GPU)."""
+import os
+import re
+
+import util
+from util import capi
+
+HEADER = os.path.join(util.ROOT, "include", "llo_cuda.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(llo_cuda_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    names = declared_symbols()
+    assert len(names) >= 30
+    lib = capi.lib()
+    for name in names:
+        assert hasattr(lib, name), "libllo_cuda.so does not export %s" % name
+
+
+def test_binding_covers_the_header():
+    assert sorted(capi.EXPORTS) == declared_symbols()
+
+
+def test_abi_version_and_error_channel():
+    lib = capi.lib()
+    assert lib.llo_cuda_abi_version() == 1
+    assert isinstance(lib.llo_cuda_last_error(), bytes)
+
+
+def test_struct_layouts_match_the_header():
+    import ctypes as C
+    assert C.sizeof(capi.Arg) == 8 + 8 * 8 + 81 * 8 + 4 + 4
+    assert C.sizeof(capi.View) == 8 + 8 * 8 + 8
+    assert C.sizeof(capi.Insn) == 2
+    assert capi.OPCODES["ABS"] == 1 and capi.OPCODES["RAND_NORM"] == 23
+    assert capi.DTYPES["DOUBLE"] == 1 and capi.DTYPES["UINT64"] == 10
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import numpy as np
+    import pytest
+    from util import llo
+    if llo.available():
+        pytest.skip("a GPU is present")
+    v = llo.variable(np.ones((2, 3)), "v")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        llo.evaluate(v)

@@ -1,6 +1,11 @@
-"""Pins the ORACLE (CPU restatement) to the reference's own golden vectors.
-CPU only.  Restates llo/test/test_operator.cpp, llo/test/test_data.cpp and
-llo/test/test_api.cpp; vectors live in tests/golden/reference_vectors.py."""
+"""The reference's own golden vectors, run against two evaluators:
+  backend "oracle": the CPU restatement (oracle/) -- this PINS the oracle
+  backend "gpu":    the CUDA path (C-ABI / llo.evaluate) -- marked gpu
+Restates llo/test/test_operator.cpp, llo/test/test_data.cpp and
+llo/test/test_api.cpp; vectors live in tests/golden/reference_vectors.py.
+Integer / index results must be bit-exact on both; floating results are
+checked to 4 ulp on the oracle (EXPECT_DOUBLE_EQ) and to 1e-12 relative on
+the GPU (the north-star fp64 tolerance)."""
 import math
 
 import numpy as np
@@ -13,57 +18,87 @@ import reference_vectors as G
 F8 = np.float64
 
 
-def ulp_close(expect, got, ulps=4):
-    """EXPECT_DOUBLE_EQ: within 4 ulp"""
-    expect = np.asarray(expect, dtype=F8)
-    got = np.asarray(got, dtype=F8)
-    assert expect.shape == got.shape
-    tol = ulps * np.spacing(np.maximum(np.abs(expect), np.abs(got)))
-    assert np.all(np.abs(expect - got) <= tol), (expect, got)
+class Backend:
+    def __init__(self, name, ctx=None):
+        self.name = name
+        self.ctx = ctx
+
+    def evaluate(self, tens, dtype=F8):
+        if self.name == "oracle":
+            return oracle.evaluate(tens, np.dtype(dtype))
+        return llo.evaluate(tens, np.dtype(dtype))
+
+    def op_exec(self, opcode, dtype, outshape, args):
+        if self.name == "oracle":
+            return util.oracle_op_exec(opcode, dtype, outshape, args)
+        return util.gpu_op_exec(self.ctx, opcode, dtype, outshape, args)
+
+    def unary(self, opcode, dtype, outshape, arg):
+        if self.name == "oracle":
+            return util.oracle_unary(opcode, dtype, outshape, arg)
+        return util.gpu_op_exec(self.ctx, opcode, dtype, outshape, [arg], entry="unary")
+
+    def close(self, expect, got):
+        expect = np.asarray(expect, dtype=F8)
+        got = np.asarray(got, dtype=F8)
+        assert expect.shape == got.shape
+        if self.name == "oracle":
+            # EXPECT_DOUBLE_EQ: within 4 ulp
+            tol = 4 * np.spacing(np.maximum(np.abs(expect), np.abs(got)))
+        else:
+            tol = 1e-12 * np.maximum(np.abs(expect), 1e-300) + 1e-300
+        assert np.all(np.abs(expect - got) <= tol), (expect, got)
+
+
+@pytest.fixture(params=["oracle", pytest.param("gpu", marks=pytest.mark.gpu)])
+def be(request):
+    if request.param == "gpu":
+        return Backend("gpu", request.getfixturevalue("ctx"))
+    return Backend("oracle")
 
 
 # ---- OPERATOR (test_operator.cpp) -------------------------------------------
 
-def test_operator_unary():
+def test_operator_unary(be):
     data = np.array(G.OP_DATA, dtype=F8)
-    out = util.oracle_unary("ABS", F8, G.OP_SHAPE, (data, G.OP_SHAPE, None, True))
+    out = be.unary("ABS", F8, G.OP_SHAPE, (data, G.OP_SHAPE, None, True))
     assert list(out) == G.OP_DATA
-    out = util.oracle_unary("ABS", F8, G.OP_REDUCED, (data, G.OP_SHAPE, G.OVERWRITE_MAP, True))
+    out = be.unary("ABS", F8, G.OP_REDUCED, (data, G.OP_SHAPE, G.OVERWRITE_MAP, True))
     assert list(out) == G.UNARY_PUSH_EXPECT
     data2 = np.array(G.UNARY_PULL_DATA, dtype=F8)
-    out = util.oracle_unary("ABS", F8, G.OP_SHAPE, (data2, G.OP_REDUCED, G.OVERWRITE_MAP, False))
+    out = be.unary("ABS", F8, G.OP_SHAPE, (data2, G.OP_REDUCED, G.OVERWRITE_MAP, False))
     assert list(out) == G.UNARY_PULL_EXPECT
 
 
-def test_operator_binary():
+def test_operator_binary(be):
     d1 = np.array(G.OP_DATA, dtype=F8)
     d2 = np.array(G.OP_DATA2, dtype=F8)
     d3 = np.array(G.OP_DATA3, dtype=F8)
     d4 = np.array(G.OP_DATA4, dtype=F8)
     M = G.OVERWRITE_MAP
-    out = util.oracle_op_exec("SUB", F8, G.OP_REDUCED, [(d1, G.OP_SHAPE, M, True), (d2, G.OP_SHAPE, M, True)])
+    out = be.op_exec("SUB", F8, G.OP_REDUCED, [(d1, G.OP_SHAPE, M, True), (d2, G.OP_SHAPE, M, True)])
     assert list(out) == G.BINARY_PUSH_PUSH
-    out = util.oracle_op_exec("SUB", F8, G.OP_EXTENDED, [(d1, G.OP_SHAPE, M, False), (d2, G.OP_SHAPE, M, False)])
+    out = be.op_exec("SUB", F8, G.OP_EXTENDED, [(d1, G.OP_SHAPE, M, False), (d2, G.OP_SHAPE, M, False)])
     assert list(out) == G.BINARY_PULL_PULL
-    out = util.oracle_op_exec("SUB", F8, G.OP_SHAPE, [(d3, G.OP_EXTENDED, M, True), (d4, G.OP_REDUCED, M, False)])
+    out = be.op_exec("SUB", F8, G.OP_SHAPE, [(d3, G.OP_EXTENDED, M, True), (d4, G.OP_REDUCED, M, False)])
     assert list(out) == G.BINARY_PUSH_PULL
-    out = util.oracle_op_exec("SUB", F8, G.OP_SHAPE, [(d4, G.OP_REDUCED, M, False), (d3, G.OP_EXTENDED, M, True)])
+    out = be.op_exec("SUB", F8, G.OP_SHAPE, [(d4, G.OP_REDUCED, M, False), (d3, G.OP_EXTENDED, M, True)])
     assert list(out) == G.BINARY_PULL_PUSH
 
 
-def test_operator_nnary():
+def test_operator_nnary(be):
     d1 = np.array(G.OP_DATA, dtype=F8)
     d2 = np.array(G.OP_DATA2, dtype=F8)
     d3 = np.array(G.OP_DATA3, dtype=F8)
     d4 = np.array(G.OP_DATA4, dtype=F8)
     M = G.OVERWRITE_MAP
-    out = util.oracle_op_exec("SUM", F8, G.OP_REDUCED, [(d1, G.OP_SHAPE, M, True), (d2, G.OP_SHAPE, M, True)])
+    out = be.op_exec("SUM", F8, G.OP_REDUCED, [(d1, G.OP_SHAPE, M, True), (d2, G.OP_SHAPE, M, True)])
     assert list(out) == G.NNARY_PUSH_PUSH
-    out = util.oracle_op_exec("SUM", F8, G.OP_EXTENDED, [(d1, G.OP_SHAPE, M, False), (d2, G.OP_SHAPE, M, False)])
+    out = be.op_exec("SUM", F8, G.OP_EXTENDED, [(d1, G.OP_SHAPE, M, False), (d2, G.OP_SHAPE, M, False)])
     assert list(out) == G.NNARY_PULL_PULL
-    out = util.oracle_op_exec("SUM", F8, G.OP_SHAPE, [(d3, G.OP_EXTENDED, M, True), (d4, G.OP_REDUCED, M, False)])
+    out = be.op_exec("SUM", F8, G.OP_SHAPE, [(d3, G.OP_EXTENDED, M, True), (d4, G.OP_REDUCED, M, False)])
     assert list(out) == G.NNARY_MIXED
-    out = util.oracle_op_exec("SUM", F8, G.OP_SHAPE, [(d4, G.OP_REDUCED, M, False), (d3, G.OP_EXTENDED, M, True)])
+    out = be.op_exec("SUM", F8, G.OP_SHAPE, [(d4, G.OP_REDUCED, M, False), (d3, G.OP_EXTENDED, M, True)])
     assert list(out) == G.NNARY_MIXED
 
 
@@ -80,31 +115,29 @@ def test_data_mismatch_size():
         v.assign(np.zeros(list(reversed(G.DATA_MISMATCH_SHAPE)), dtype=np.int32))
 
 
-def test_data_source_retype():
+def test_data_source_retype(be):
     src = var(G.RETYPE_DATA, G.RETYPE_SHAPE)
-    got = oracle.evaluate(src, np.dtype(np.uint16))
+    got = be.evaluate(src, np.uint16)
     assert got.dtype == np.uint16
     assert list(reversed(got.shape)) == G.RETYPE_SHAPE
     assert list(flat(got)) == [int(v) for v in G.RETYPE_DATA]
 
 
-def test_data_placeholder():
+def test_data_placeholder(be):
     pl = llo.variable(np.zeros(list(reversed(G.PLACEHOLDER_SHAPE))), "pl")
-    got = oracle.evaluate(pl, np.dtype(F8))
+    got = be.evaluate(pl, F8)
     assert list(reversed(got.shape)) == G.PLACEHOLDER_SHAPE
     assert np.all(flat(got) == 0)
     pl.assign(np.array(G.PLACEHOLDER_DATA, dtype=F8).reshape(list(reversed(G.PLACEHOLDER_SHAPE))))
-    got = oracle.evaluate(pl, np.dtype(F8))
+    got = be.evaluate(pl, F8)
     assert list(flat(got)) == G.PLACEHOLDER_DATA
 
 
 # ---- API (test_api.cpp) -----------------------------------------------------
 
-def ev(t, dtype=F8):
-    return oracle.evaluate(t, np.dtype(dtype))
 
-
-def check_unary_elementary(op, fwd, bwd):
+def check_unary_elementary(be, op, fwd, bwd):
+    ev, ulp_close = be.evaluate, be.close
     src = var(G.UNARY_DATA, G.UNARY_SHAPE)
     dest = op(src)
     out = ev(dest)
@@ -129,11 +162,12 @@ UNARY_CASES = {
 
 
 @pytest.mark.parametrize("name", sorted(UNARY_CASES))
-def test_api_unary(name):
-    check_unary_elementary(*UNARY_CASES[name])
+def test_api_unary(be, name):
+    check_unary_elementary(be, *UNARY_CASES[name])
 
 
-def check_binary_elementary(op, fwd, bwd, dtype=F8, data=None, data2=None, shape=None, exact=False):
+def check_binary_elementary(be, op, fwd, bwd, dtype=F8, data=None, data2=None, shape=None, exact=False):
+    ev, ulp_close = be.evaluate, be.close
     data = G.BINARY_DATA if data is None else data
     data2 = G.BINARY_DATA2 if data2 is None else data2
     shape = G.BINARY_SHAPE if shape is None else shape
@@ -174,8 +208,8 @@ BINARY_CASES = {
 
 
 @pytest.mark.parametrize("name", sorted(BINARY_CASES))
-def test_api_binary(name):
-    check_binary_elementary(*BINARY_CASES[name])
+def test_api_binary(be, name):
+    check_binary_elementary(be, *BINARY_CASES[name])
 
 
 INT_CASES = {
@@ -187,14 +221,15 @@ INT_CASES = {
 
 
 @pytest.mark.parametrize("name", sorted(INT_CASES))
-def test_api_compare_int(name):
+def test_api_compare_int(be, name):
     op, fwd = INT_CASES[name]
-    check_binary_elementary(op, fwd, lambda a, b, l, r: 0, dtype=np.int32,
+    check_binary_elementary(be, op, fwd, lambda a, b, l, r: 0, dtype=np.int32,
                             data=G.BINARY_INT_DATA, data2=G.BINARY_INT_DATA2,
                             shape=G.BINARY_INT_SHAPE, exact=True)
 
 
-def test_api_flip():
+def test_api_flip(be):
+    ev, ulp_close = be.evaluate, be.close
     src = var(G.FLIP_DATA, G.FLIP_SHAPE)
     dest = age.flip(src, 1)
     out = ev(dest)
@@ -205,7 +240,8 @@ def test_api_flip():
     assert np.all(flat(g) == 1) and list(reversed(g.shape)) == G.FLIP_SHAPE
 
 
-def check_generic(op, verify, bwverify):
+def check_generic(be, op, verify, bwverify):
+    ev = be.evaluate
     src = var(G.GENERIC_DATA, G.GENERIC_SHAPE)
     dest = op(src)
     verify(ev(dest))
@@ -214,14 +250,16 @@ def check_generic(op, verify, bwverify):
     bwverify(flat(g))
 
 
-def test_api_nelems_ndims():
-    check_generic(age.n_elems, lambda out: (out.size == 1 and flat(out)[0] == 24) or pytest.fail(str(out)),
+def test_api_nelems_ndims(be):
+    ev, ulp_close = be.evaluate, be.close
+    check_generic(be, age.n_elems, lambda out: (out.size == 1 and flat(out)[0] == 24) or pytest.fail(str(out)),
                   lambda g: np.testing.assert_array_equal(g, 0))
-    check_generic(lambda s: age.n_dims(s, 2), lambda out: flat(out)[0] == 4 or pytest.fail(str(out)),
+    check_generic(be, lambda s: age.n_dims(s, 2), lambda out: flat(out)[0] == 4 or pytest.fail(str(out)),
                   lambda g: np.testing.assert_array_equal(g, 0))
 
 
-def test_api_reductions():
+def test_api_reductions(be):
+    ev, ulp_close = be.evaluate, be.close
     d = np.array(G.GENERIC_DATA, dtype=F8)
 
     def scalar(expect):
@@ -233,14 +271,15 @@ def test_api_reductions():
     total = 0.0
     for v in G.GENERIC_DATA:
         total += v
-    check_generic(age.reduce_sum0, scalar(total), lambda g: np.testing.assert_array_equal(g, 1))
-    check_generic(age.reduce_min0, scalar(d.min()),
+    check_generic(be, age.reduce_sum0, scalar(total), lambda g: np.testing.assert_array_equal(g, 1))
+    check_generic(be, age.reduce_min0, scalar(d.min()),
                   lambda g: np.testing.assert_array_equal(g, (d == d.min()).astype(F8)))
-    check_generic(age.reduce_max0, scalar(d.max()),
+    check_generic(be, age.reduce_max0, scalar(d.max()),
                   lambda g: np.testing.assert_array_equal(g, (d == d.max()).astype(F8)))
 
 
-def test_api_permute():
+def test_api_permute(be):
+    ev, ulp_close = be.evaluate, be.close
     src = var(G.PERMUTE_DATA, G.PERMUTE_SHAPE)
     dest = age.permute(src, G.PERMUTE_ORDER)
     out = ev(dest)
@@ -257,7 +296,8 @@ def test_api_permute():
     assert list(reversed(g.shape)) == G.PERMUTE_SHAPE and np.all(flat(g) == 1)
 
 
-def test_api_extend():
+def test_api_extend(be):
+    ev, ulp_close = be.evaluate, be.close
     src = var(G.EXTEND_DATA, G.EXTEND_SHAPE)
     dest = age.extend(src, len(G.EXTEND_SHAPE), G.EXTEND_EXT)
     out = flat(ev(dest))
@@ -270,7 +310,8 @@ def test_api_extend():
     assert list(reversed(g.shape)) == G.EXTEND_SHAPE and np.all(flat(g) == 3)
 
 
-def test_api_matmul():
+def test_api_matmul(be):
+    ev, ulp_close = be.evaluate, be.close
     a = var(G.MATMUL_A, G.MATMUL_ASHAPE, np.int32)
     b = var(G.MATMUL_B, G.MATMUL_BSHAPE, np.int32)
     dest = age.matmul(a, b)
@@ -288,7 +329,8 @@ def test_api_matmul():
     assert list(reversed(gb.shape)) == G.MATMUL_BSHAPE and list(flat(gb)) == G.MATMUL_GB
 
 
-def test_api_convolution():
+def test_api_convolution(be):
+    ev, ulp_close = be.evaluate, be.close
     img = var(G.CONV_IMG, G.CONV_ISHAPE)
     kernel = var(G.CONV_KERNEL, G.CONV_KSHAPE)
     dest = age.convolution(img, kernel)
@@ -307,7 +349,8 @@ def _moments(x):
     return mean, (x * x).mean() - mean * mean
 
 
-def test_api_rand_binomial():
+def test_api_rand_binomial(be):
+    ev, ulp_close = be.evaluate, be.close
     n, p = 3.2234, 0.2547977589
     src = var([n], []); src2 = var([p], [])
     dest = age.functor_extended("RAND_BINO", [src, src2], 0, G.RAND_SHAPE)
@@ -322,7 +365,8 @@ def test_api_rand_binomial():
     assert flat(ev(llo.derive(dest, src2)))[0] == 0
 
 
-def test_api_rand_uniform():
+def test_api_rand_uniform(be):
+    ev, ulp_close = be.evaluate, be.close
     hi, lo = 3.2234, 0.2547977589
     src = var([lo], []); src2 = var([hi], [])
     dest = age.functor_extended("RAND_UNIF", [src, src2], 0, G.RAND_UNIF_SHAPE)
@@ -332,7 +376,8 @@ def test_api_rand_uniform():
     assert flat(ev(llo.derive(dest, src)))[0] == 0
 
 
-def test_api_rand_normal():
+def test_api_rand_normal(be):
+    ev, ulp_close = be.evaluate, be.close
     mu, sd = 3.2234, 1.2547977589
     src = var([mu], []); src2 = var([sd], [])
     dest = age.functor_extended("RAND_NORM", [src, src2], 0, G.RAND_SHAPE)
