@@ -63,10 +63,11 @@ index_table_kernel (int64_t* __restrict__ table,
 			}
 			if (acc < 0)
 			{
-				acc = limit + acc;
-				if (acc < 0)
+				// same floored-modulo wrap as ade::index on the host
+				acc = acc - limit * floor(acc / limit);
+				if (acc >= limit)
 				{
-					bad = true;
+					acc = limit - 1;
 				}
 			}
 			idx = idx * (int64_t) p.to[j] + (bad ? 0 : (int64_t) acc);

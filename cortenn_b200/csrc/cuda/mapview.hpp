@@ -104,13 +104,13 @@ inline MapKind classify_map (const double m[LLO_MAT],
 			}
 		}
 		double limit = (double) to[j];
-		if (hi >= limit || lo < -limit)
+		if (hi >= limit)
 		{
 			return MAP_INVALID;
 		}
 		if (1 == to[j])
 		{
-			// every value in [-1, 1) wraps / truncates to coordinate 0
+			// every value below 1 wraps / truncates to coordinate 0
 			continue;
 		}
 		if (false == integral)
@@ -120,11 +120,11 @@ inline MapKind classify_map (const double m[LLO_MAT],
 		int64_t shift = 0;
 		if (lo < 0)
 		{
-			if (hi >= 0)
+			if (hi >= 0 || lo < -limit)
 			{
-				return MAP_GENERAL; // only part of the range wraps
+				return MAP_GENERAL; // the range wraps unevenly
 			}
-			shift = (int64_t) to[j]; // whole range wraps from the end
+			shift = (int64_t) to[j]; // whole range wraps once from the end
 		}
 		out.offset += ((int64_t) m[8 * 9 + j] + shift) * tostride[j];
 		for (int i = 0; i < LLO_RANK; ++i)

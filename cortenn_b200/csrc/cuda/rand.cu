@@ -98,8 +98,10 @@ rand_kernel (int opcode, const __grid_constant__ RandParams p)
 	{
 		T a[1];
 		B b[1];
-		vm_load<T,1>(a, p.view, p.view.in[0], i, 1);
-		vm_load<B,1>(b, p.view, p.view.in[1], i, 1);
+		FlatLoader<T,1> load_a = {p.view, i, 1};
+		FlatLoader<B,1> load_b = {p.view, i, 1};
+		load_a.load(a, 0);
+		load_b.load(b, 1);
 		uint32_t r[4];
 		philox4(r, p.seed, p.offset + i, 0);
 		T result;

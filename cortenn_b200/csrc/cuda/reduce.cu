@@ -735,3 +735,40 @@ extern "C" int llo_cuda_elementwise_reduce (llo_cuda_ctx*, int, void*,
 {
 	return fail(LLO_ERR_FATAL, "llo_cuda_elementwise_reduce: not built yet");
 }
+
+extern "C" int llo_cuda_reduce_view (llo_cuda_ctx* ctx, int opcode, int dtype,
+	void* out, const uint64_t outshape[LLO_RANK], const llo_cuda_view* src,
+	int nfold, const uint64_t* fold_size, const int64_t* fold_stride,
+	int accumulate, int mode)
+{
+	if (nfold < 0 || nfold > LLO_RANK)
+	{
+		return fail(LLO_ERR_FATAL, "cannot fold %d dimensions", nfold);
+	}
+	ReduceDesc desc;
+	desc.nfold = 0;
+	desc.inv.offset = src->offset;
+	for (int d = 0; d < LLO_RANK; ++d)
+	{
+		desc.outshape[d] = outshape[d];
+		desc.inv.stride[d] = outshape[d] > 1 ? src->stride[d] : 0;
+	}
+	for (int k = 0; k < nfold; ++k)
+	{
+		if (fold_size[k] > 1)
+		{
+			desc.fold_size[desc.nfold] = fold_size[k];
+			desc.fold_stride[desc.nfold] = fold_stride[k];
+			++desc.nfold;
+		}
+	}
+	if (0 == desc.nfold)
+	{
+		// nothing to fold: a strided copy (or accumulate) of the view
+		desc.fold_size[0] = 1;
+		desc.fold_stride[0] = 0;
+		desc.nfold = 1;
+	}
+	return reduce_launch(ctx, opcode, dtype, out, src->data, desc,
+		accumulate, mode);
+}

@@ -177,8 +177,8 @@ inline CoordT coordinate (const Shape& shape, NElemT idx)
 }
 
 /// Coordinate -> linear index.  Real coordinates are accepted: a negative
-/// coordinate wraps once from the end of its dimension, then the value is
-/// truncated toward zero (0.5 -> 0, 1.5 -> 1: llo/test/test_operator.cpp:42-48)
+/// coordinate wraps from the end of its dimension (floored modulo), then
+/// the value is truncated toward zero (0.5 -> 0, 1.5 -> 1: llo/test/test_operator.cpp:42-48)
 inline NElemT index (const Shape& shape, const CoordT& coord)
 {
 	NElemT idx = 0;
@@ -194,13 +194,13 @@ inline NElemT index (const Shape& shape, const CoordT& coord)
 		}
 		if (c < 0)
 		{
-			c = limit + c;
-			if (c < 0)
+			// python-style wrap from the end of the dimension, any number
+			// of periods (flip maps use -c - 1; the convolution's kernel
+			// map reaches below -limit on size-1 dims)
+			c = c - limit * std::floor(c / limit);
+			if (c >= limit)
 			{
-				logs::fatalf(
-					"cannot get index of bad coordinate %s for shape %s",
-					fmts::to_string(coord.begin(), coord.end()).c_str(),
-					shape.to_string().c_str());
+				c = limit - 1;
 			}
 		}
 		idx = idx * shape.at(k) + (NElemT) c;

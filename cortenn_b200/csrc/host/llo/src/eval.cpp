@@ -1,4 +1,6 @@
 #include "llo/eval.hpp"
+#include "llo/plan.hpp"
+#include "llo/session.hpp"
 
 #ifdef LLO_EVAL_HPP
 
@@ -78,6 +80,10 @@ void Evaluator::visit (ade::iFunctor* func)
 
 GenericData eval_device (ade::TensptrT tens, age::_GENERATED_DTYPE dtype)
 {
+	if (0 != get_option("plan"))
+	{
+		return planned_eval(tens, dtype);
+	}
 	Evaluator eval(dtype);
 	tens->accept(eval);
 	return eval.out_;

@@ -22,6 +22,7 @@
 
 #include "llo/llo.hpp"
 #include "llo/session.hpp"
+#include "llo/plan.hpp"
 
 #include "dbg/ade.hpp"
 
@@ -349,6 +350,21 @@ PYBIND11_MODULE(_C, m)
 		{ return llo_cuda_launch_count(llo::device::ctx()); });
 	llo_m.def("context", []()
 		{ return (uintptr_t) llo::device::ctx(); });
+	llo_m.def("plan_stats", []()
+		{
+			const llo::PlanStats& st = llo::last_plan_stats();
+			py::dict out;
+			out["nodes"] = st.nodes_;
+			out["views"] = st.views_;
+			out["consts"] = st.consts_;
+			out["fused"] = st.fused_;
+			out["programs"] = st.programs_;
+			out["reduces"] = st.reduces_;
+			out["gemms"] = st.gemms_;
+			out["generic"] = st.generic_;
+			out["simplified"] = st.simplified_;
+			return out;
+		});
 	llo_m.def("set_option", &llo::set_option);
 	llo_m.def("get_option", &llo::get_option);
 }

@@ -172,9 +172,20 @@ int llo_cuda_elementwise (llo_cuda_ctx* ctx, int dtype, void* out,
 	const llo_cuda_view* inputs, int ninputs,
 	const double* consts, int nconsts,
 	const llo_cuda_insn* program, int ninsns);
-/* Same program, but the result is folded over output dims >= first_dim
- * with `reduce_opcode` (SUM PROD MIN MAX) instead of being stored:
- * out has shape outshape[0:first_dim]. */
+/* Reduction straight from a view: out[o] = fold over r of
+ * src.data[src.offset + sum_d o_d*src.stride[d] + sum_k r_k*fold_stride[k]],
+ * o over `outshape`, r over `fold_size` with fold dim 0 fastest (the
+ * reference's accumulation order).  This is nnary's push branch
+ * (operator.hpp:376-393) for a reduce map whose argument is itself a
+ * permuted / strided view (e.g. reduce_sum(permute(x,{1,0}),1)), without
+ * materialising the view.  accumulate: 1 = fold into the values in `out`. */
+int llo_cuda_reduce_view (llo_cuda_ctx* ctx, int opcode, int dtype, void* out,
+	const uint64_t outshape[LLO_RANK], const llo_cuda_view* src,
+	int nfold, const uint64_t* fold_size, const int64_t* fold_stride,
+	int accumulate, int mode);
+/* Same program as llo_cuda_elementwise, but the result is folded over output
+ * dims >= first_dim with `reduce_opcode` (SUM PROD MIN MAX) instead of being
+ * stored: out has shape outshape[0:first_dim]. */
 int llo_cuda_elementwise_reduce (llo_cuda_ctx* ctx, int dtype, void* out,
 	const uint64_t outshape[LLO_RANK], int first_dim, int reduce_opcode,
 	const llo_cuda_view* inputs, int ninputs,

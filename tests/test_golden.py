@@ -386,3 +386,25 @@ def test_api_rand_normal(be):
     assert abs(mu - mean) / mean < 0.1
     assert abs(sd * sd - variance) / variance < 0.1
     assert flat(ev(llo.derive(dest, src2)))[0] == 0
+
+
+def test_api_convolution_matches_a_direct_convolution(be):
+    """llo/test/ptest.py:441-490 checks age.convolution against
+    tf.nn.convolution(padding="VALID"); TensorFlow is not available here, so
+    the same NHWC x HWIO correlation is written out in numpy.  Pins the
+    negative-coordinate wrap of ade::index beyond one period (kernel maps
+    reach -(out_h - 1) on size-1 dims)."""
+    rng = np.random.default_rng(5)
+    for shape, kshape in (([1, 3, 3, 1], [3, 3, 1, 1]), ([2, 5, 5, 3], [3, 3, 3, 4])):
+        data = rng.uniform(0, 1, shape)
+        kernel = rng.uniform(0, 1, kshape)
+        out = be.evaluate(age.convolution(llo.variable(data, "img"), llo.variable(kernel, "k")))
+        nb, ih, iw, ic = shape
+        kh, kw, _, oc = kshape
+        oh, ow = ih - 2 * (kh // 2), iw - 2 * (kw // 2)
+        expect = np.zeros((nb, oh, ow, oc))
+        for y in range(oh):
+            for x in range(ow):
+                patch = data[:, y:y + kh, x:x + kw, :]
+                expect[:, y, x, :] = np.tensordot(patch, kernel, axes=([1, 2, 3], [0, 1, 2]))
+        np.testing.assert_allclose(np.asarray(out).reshape(expect.shape), expect, rtol=1e-12)

@@ -1,0 +1,269 @@
+"""GPU parity, graph level: llo.evaluate (planner: views, fused programs,
+reductions from views, GEMM lowering) and the literal one-call-per-functor
+mode, against the CPU oracle on the same ade graphs."""
+import numpy as np
+import pytest
+
+import util
+from util import age, llo, oracle, var
+
+pytestmark = pytest.mark.gpu
+
+F4, F8, I4, I8 = np.float32, np.float64, np.int32, np.int64
+
+
+def tol_of(dtype):
+    return {F4: 1e-6, F8: 1e-12}.get(dtype, 0)
+
+
+def check(node, dtype, scale_tol=1.0, what=""):
+    got = llo.evaluate(node, np.dtype(dtype))
+    want = oracle.evaluate(node, np.dtype(dtype))
+    assert got.shape == want.shape, what
+    tol = tol_of(dtype) * scale_tol
+    if tol == 0:
+        np.testing.assert_array_equal(want, got, err_msg=what)
+    else:
+        w = want.astype(np.float64)
+        g = got.astype(np.float64)
+        assert (np.isnan(w) == np.isnan(g)).all(), what
+        fin = np.isfinite(w)
+        err = np.abs(w[fin] - g[fin])
+        assert (err <= tol * np.maximum(np.abs(w[fin]), 1.0)).all(), \
+            "%s: max rel err %g" % (what, (err / np.maximum(np.abs(w[fin]), 1.0)).max())
+    return got
+
+
+@pytest.fixture(params=[1, 0], ids=["planned", "literal"])
+def mode(request):
+    llo.set_option("plan", request.param)
+    yield request.param
+    llo.set_option("plan", 1)
+
+
+def rnd(rng, shape, dtype, lo=0.5, hi=2.0):
+    if np.issubdtype(dtype, np.floating):
+        return rng.uniform(lo, hi, shape).astype(dtype)
+    return rng.integers(1, 9, shape).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", [F4, F8, I4])
+def test_chain_with_broadcast_and_permute(mode, dtype):
+    rng = np.random.default_rng(3)
+    d = 96
+    x = llo.variable(rnd(rng, (d, d), dtype), "x")
+    b = llo.variable(rnd(rng, (d,), dtype), "b")
+    first = age.exp(x) if dtype != I4 else age.abs(x)
+    root = age.add(age.mul(first, age.extend(b, 1, [d])), age.permute(x, [1, 0]))
+    check(root, dtype, what="chain")
+    if mode == 1:
+        st = llo.plan_stats()
+        assert st["programs"] == 1 and st["views"] >= 2 and st["generic"] == 0, st
+
+
+@pytest.mark.parametrize("dtype", [F4, F8, I8])
+def test_reductions_of_views(mode, dtype):
+    rng = np.random.default_rng(5)
+    x = llo.variable(rnd(rng, (40, 72), dtype, 0.0, 1.0), "x")   # ade [72, 40]
+    for op in (age.reduce_sum, age.reduce_max, age.reduce_min):
+        check(op(x, 1), dtype, what="columns")
+        check(op(x, 0), dtype, what="all")
+        check(op(age.permute(x, [1, 0]), 1), dtype, what="rows via permute")
+    if mode == 1:
+        st = llo.plan_stats()
+        assert st["reduces"] == 1 and st["programs"] == 0, st  # permute never materialised
+    check(age.reduce_prod(age.add(x, x), 1), dtype, scale_tol=50, what="prod of fused")
+    check(age.reduce_mean(x), dtype, what="mean")
+
+
+@pytest.mark.parametrize("dtype", [F4, F8, I4, I8])
+@pytest.mark.parametrize("mnk", [(7, 5, 3), (64, 48, 80), (130, 70, 257)])
+def test_matmul_lowers_to_gemm(dtype, mnk):
+    m, n, k = mnk
+    rng = np.random.default_rng(7)
+    if np.issubdtype(dtype, np.integer):
+        a = rng.integers(-8, 9, (n, k)).astype(dtype)
+        b = rng.integers(-8, 9, (k, m)).astype(dtype)
+    else:
+        a = rng.uniform(-1, 1, (n, k)).astype(dtype)
+        b = rng.uniform(-1, 1, (k, m)).astype(dtype)
+    va, vb = llo.variable(a, "a"), llo.variable(b, "b")
+    root = age.matmul(va, vb)
+    llo.set_option("plan", 1)
+    got = llo.evaluate(root, np.dtype(dtype))
+    st = llo.plan_stats()
+    assert st["gemms"] == 1 and st["programs"] == 0, st
+    if np.issubdtype(dtype, np.integer):
+        np.testing.assert_array_equal(a.astype(np.int64) @ b.astype(np.int64), got.astype(np.int64))
+    else:
+        exact = a.astype(np.float64) @ b.astype(np.float64)
+        scale = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+        assert (np.abs(exact - got) <= tol_of(dtype) * scale).all()
+    if m * n * k <= 64 * 48 * 80:
+        # the reference's own materialised [M,N,C] evaluation
+        want = oracle.evaluate(root, np.dtype(dtype))
+        if np.issubdtype(dtype, np.integer):
+            np.testing.assert_array_equal(want, got)
+        else:
+            scale = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+            assert (np.abs(want.astype(np.float64) - got) <= 4 * tol_of(dtype) * scale).all()
+
+
+@pytest.mark.parametrize("dtype", [F4, F8, I4])
+def test_matmul_gradients(mode, dtype):
+    rng = np.random.default_rng(11)
+    n, k, m = 12, 9, 7
+    if np.issubdtype(dtype, np.integer):
+        a = rng.integers(1, 9, (n, k)).astype(dtype)
+        b = rng.integers(1, 9, (k, m)).astype(dtype)
+    else:
+        a = rng.uniform(0.5, 2, (n, k)).astype(dtype)
+        b = rng.uniform(0.5, 2, (k, m)).astype(dtype)
+    va, vb = llo.variable(a, "a"), llo.variable(b, "b")
+    root = age.matmul(va, vb)
+    for target in (va, vb):
+        grad = llo.derive(root, target)
+        check(grad, dtype, scale_tol=8, what="d matmul")
+        if mode == 1:
+            st = llo.plan_stats()
+            assert st["gemms"] >= 1 or st["reduces"] >= 1, st
+    # matmul(c, c): both paths to the same leaf
+    c = llo.variable(rnd(rng, (6, 6), dtype), "c")
+    check(llo.derive(age.matmul(c, c), c), dtype, scale_tol=8, what="d matmul(c,c)")
+
+
+def mlp(dtype, batch=24, sizes=(10, 16, 12, 4), seed=13):
+    rng = np.random.default_rng(seed)
+    x = llo.variable(rng.uniform(0.05, 1, (batch, sizes[0])).astype(dtype), "X")
+    y = llo.variable(rng.uniform(0, 1, (batch, sizes[-1])).astype(dtype), "Y")
+    params = []
+    h = x
+    for i in range(len(sizes) - 1):
+        w = llo.variable((rng.standard_normal((sizes[i], sizes[i + 1])) / np.sqrt(sizes[i])).astype(dtype), "W%d" % i)
+        b = llo.variable((0.1 * rng.standard_normal((sizes[i + 1],))).astype(dtype), "b%d" % i)
+        params += [w, b]
+        z = age.add(age.matmul(h, w), age.extend(b, 1, [batch]))
+        one = llo.scalar(1.0, [batch, sizes[i + 1]])
+        h = age.div(one, age.add(one, age.exp(age.neg(z))))
+    diff = age.sub(h, y)
+    loss = age.div(age.reduce_sum0(age.pow(diff, llo.scalar(2.0, [batch, sizes[-1]]))),
+                   llo.scalar(float(batch), []))
+    return loss, params
+
+
+@pytest.mark.parametrize("dtype", [F4, F8])
+def test_mlp_loss_and_gradients(mode, dtype):
+    loss, params = mlp(dtype)
+    check(loss, dtype, scale_tol=20, what="loss")
+    for p in params:
+        grad = llo.derive(loss, p)
+        check(grad, dtype, scale_tol=200, what="grad")
+    if mode == 1:
+        st = llo.plan_stats()
+        assert st["generic"] == 0, st
+
+
+def test_mlp_gradients_use_gemm_not_the_materialised_product():
+    loss, params = mlp(F4, batch=32, sizes=(20, 24, 16, 6))
+    llo.set_option("plan", 1)
+    llo.evaluate(llo.derive(loss, params[0]), np.dtype(F4))
+    st = llo.plan_stats()
+    assert st["gemms"] >= 5, st          # 3 forward + backward contractions
+    assert st["simplified"] > 0, st
+
+
+def test_exact_mode_keeps_the_product_rule(mode):
+    """simplify = 0: (x*y)/x is evaluated as written (NaN at x == 0 like the
+    reference); simplify = 1 rewrites it to y"""
+    a = llo.variable(np.array([[0.0, 2.0], [3.0, 4.0]]), "a")
+    b = llo.variable(np.array([[5.0, 6.0], [7.0, 8.0]]), "b")
+    grad = llo.derive(age.mul(a, b), a)
+    llo.set_option("simplify", 0)
+    try:
+        got = llo.evaluate(grad, np.dtype(F8))
+        want = oracle.evaluate(grad, np.dtype(F8))
+        np.testing.assert_array_equal(np.isnan(want), np.isnan(got))
+        np.testing.assert_array_equal(want[~np.isnan(want)], got[~np.isnan(got)])
+        assert np.isnan(got[0, 0])
+    finally:
+        llo.set_option("simplify", 1)
+    if mode == 1:
+        got = llo.evaluate(grad, np.dtype(F8))
+        np.testing.assert_array_equal(got, [[5.0, 6.0], [7.0, 8.0]])
+
+
+def test_shared_subgraphs_are_evaluated_once():
+    x = llo.variable(np.random.default_rng(17).uniform(0.5, 2, (64, 64)).astype(F4), "x")
+    shared = age.exp(age.sin(x))
+    root = age.add(age.mul(shared, shared), age.sub(shared, x))
+    llo.set_option("plan", 1)
+    before = llo.launch_count()
+    check(root, F4, what="shared")
+    # one program for `shared` (two consumers), one for the root
+    assert llo.plan_stats()["programs"] == 2
+    assert llo.launch_count() - before == 2
+
+
+def test_random_expression_graphs(mode):
+    rng = np.random.default_rng(19)
+    unary = [age.abs, age.neg, age.sin, age.cos, age.exp, age.sqrt, age.round, age.log]
+    binary = [age.add, age.sub, age.mul, age.div, age.pow, age.lt, age.gt,
+              lambda a, b: age.min([a, b]), lambda a, b: age.max([a, b])]
+    for trial in range(12):
+        shape = [int(rng.integers(2, 9)) for _ in range(int(rng.integers(1, 4)))]
+        leaves = [llo.variable(rng.uniform(0.6, 1.8, shape), "v%d" % i) for i in range(3)]
+        pool = list(leaves)
+        for _ in range(int(rng.integers(3, 10))):
+            if rng.random() < 0.4:
+                node = unary[int(rng.integers(len(unary)))](age.abs(pool[int(rng.integers(len(pool)))]))
+            else:
+                a = pool[int(rng.integers(len(pool)))]
+                b = pool[int(rng.integers(len(pool)))]
+                node = binary[int(rng.integers(len(binary)))](age.abs(a), age.abs(b))
+            # keep magnitudes tame so pow / exp stay finite
+            pool.append(age.add(age.div(node, age.add(age.abs(node), leaves[0])), leaves[1]))
+        root = pool[-1]
+        check(root, F8, scale_tol=100, what="random graph %d" % trial)
+        check(llo.derive(root, leaves[0]), F8, scale_tol=1e4, what="random grad %d" % trial)
+
+
+def test_int_types_through_graphs(mode):
+    rng = np.random.default_rng(23)
+    for dtype in (np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64):
+        a = llo.variable(rng.integers(1, 7, (5, 6)).astype(dtype), "a")
+        b = llo.variable(rng.integers(1, 7, (5, 6)).astype(dtype), "b")
+        root = age.add(age.mul(a, age.permute(age.permute(b, [1, 0]), [1, 0])),
+                       age.extend(age.reduce_max(age.sub(age.add(a, b), b), 1), 1, [5]))
+        check(root, dtype, what=str(dtype))
+        check(age.lt(a, b), dtype)
+        check(age.pow(a, age.eq(a, b)), dtype)
+
+
+def test_leaf_retype_and_constants(mode):
+    data = np.array([[1.5, 2.5, -3.5], [4.25, 5.75, 6.0]])
+    v = llo.variable(data, "v")
+    for dtype in (np.uint16, np.int32, np.float32):
+        check(age.add(v, llo.scalar(2.0, [2, 3])), dtype)
+        check(v, dtype)
+    check(age.n_elems(v), F8)
+    check(age.mul(age.n_dims(v, 0), llo.scalar(3.0, [])), F8)
+
+
+def test_rand_nodes_draw_per_visit_and_stay_in_range(mode):
+    lo = llo.variable(np.array(2.0), "lo")
+    hi = llo.variable(np.array(5.0), "hi")
+    r = age.functor_extended("RAND_UNIF", [lo, hi], 0, [50, 40])
+    llo.seed(5)
+    both = llo.evaluate(age.sub(r, r), np.dtype(F8))   # two visits, two draws (llo/eval.hpp:77-87)
+    assert np.abs(both).max() > 0.1
+    vals = llo.evaluate(r, np.dtype(F8))
+    assert vals.min() > 2.0 and vals.max() < 5.0
+
+
+def test_convolution_through_the_general_path(mode):
+    rng = np.random.default_rng(29)
+    img = llo.variable(rng.uniform(0, 1, (2, 5, 5, 3)), "img")       # [batch, w, h, in]
+    kernel = llo.variable(rng.uniform(0, 1, (3, 3, 3, 4)), "k")      # [kw, kh, in, out]
+    root = age.convolution(img, kernel)
+    check(root, F8, scale_tol=100, what="convolution")
+    check(llo.derive(root, kernel), F8, scale_tol=100, what="d convolution")
