@@ -17,7 +17,7 @@ try:
 except ImportError as exc:  # pragma: no cover - build problem, fail loudly
     raise ImportError(
         "cortenn_b200: native extension missing or unloadable (%s). "
-        "Run `python -m cortenn_b200.build` (needs nvcc + g++); there is no "
+        "Run `python cortenn_b200/build.py` (needs nvcc + g++); there is no "
         "pure-python or CPU fallback." % (exc,)) from exc
 
 from . import age, llo, capi  # noqa: E402,F401
