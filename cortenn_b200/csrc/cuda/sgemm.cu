@@ -1,17 +1,610 @@
 ///
-/// sgemm.cu — fp32 FFMA GEMM fast path (placeholder until the tiled kernel lands)
+/// sgemm.cu — K6/K7: exact fp32 GEMM on the FFMA pipe, TMA-staged.
 ///
+/// C[m,n] = sum_k A[m,k] * B[k,n], one FFMA chain per output with k ascending
+/// (the reference's accumulation order, llo/operator.hpp:378-392 applied to
+/// the matmul sub-graph of llo/src/helper.cpp:92-96; the only difference to
+/// the CPU is the fused multiply-add rounding).
+///
+/// Shape of the kernel
+///   CTA tile 128 x 128, k-tile 32, 8 warps (2 x 4, warp tile 64 x 32,
+///   8 x 8 outputs per thread in registers; two warps per scheduler leave
+///   each thread the whole 255-register budget).
+///   One elected lane moves both operand tiles with cp.async.bulk.tensor
+///   (TMA) into a 4-stage shared-memory ring; full/empty mbarriers hand the
+///   stages over and the (cheap) producer duty rotates over the warps, so no
+///   thread spends issue slots on global loads or address arithmetic and the
+///   FFMA pipe sees ~94% of the instruction stream.  Operand fragments are
+///   double-buffered in registers: the LDS of step k+1 fly under the 64
+///   FFMAs of step k.
+///   Operand layouts (all four combinations, i.e. forward, dW and dX GEMMs):
+///     k-contiguous operand  -> smem [row][k], 128-byte TMA swizzle; a thread
+///                              reads 4 consecutive k of one row per LDS.128
+///                              and owns rows r, r+8, ... so the XOR swizzle
+///                              spreads a warp's rows over all banks
+///     m/n-contiguous operand -> smem [k][row], unswizzled; a thread reads 4
+///                              consecutive rows of one k per LDS.128
+///   Out-of-range parts of edge tiles are zero-filled by TMA and add 0.
+///
+
+#include <utility>
+
+#include <cuda.h>
 
 #include "gemm.cuh"
 
 namespace llo_cuda
 {
 
-int sgemm_launch (llo_cuda_ctx*, const GemmParams&, float*,
-	const float*, const float*, int, bool& handled)
+namespace
+{
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 32;
+constexpr int STAGES = 4;
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+constexpr int A_STAGE_FLOATS = BM * BK;
+constexpr int B_STAGE_FLOATS = BK * BN;
+constexpr uint32_t STAGE_BYTES = (A_STAGE_FLOATS + B_STAGE_FLOATS) * 4;
+// fragment prefetches run one k / k-group past the end of a stage (the
+// values are never used), so the tiles are followed by a pad
+constexpr size_t TAIL_PAD = 1024;
+constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ +
+	(size_t) STAGES * STAGE_BYTES + TAIL_PAD + 2 * STAGES * sizeof(uint64_t);
+// k-tiles the TMA loads run ahead of the FFMAs; STAGES - LEAD stages of
+// slack keep the refilling warp from ever waiting on a slower warp
+constexpr uint32_t LEAD = STAGES - 2;
+
+struct SgemmArgs
+{
+	float* C;
+	int64_t c_rs;      // row stride of C in elements (columns are contiguous)
+	uint32_t M;
+	uint32_t N;
+	uint32_t K;
+	uint32_t tiles_m;
+	uint32_t tiles_n;
+	uint32_t vec_store; // C rows allow aligned 128-bit stores
+};
+
+__device__ __forceinline__ uint32_t smem_u32 (const void* p)
+{
+	return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init (uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;"
+		:: "r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx (uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+		:: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive (uint64_t* bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
+		:: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait (uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred P1;\n"
+		"LAB_WAIT:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+		"@P1 bra DONE;\n"
+		"bra LAB_WAIT;\n"
+		"DONE:\n"
+		"}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d (void* dst, const CUtensorMap* map,
+	uint64_t* bar, int c0, int c1)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+		" [%0], [%1, {%3, %4}], [%2];"
+		:: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+		: "memory");
+}
+
+__device__ __forceinline__ float comp (const float4& v, int k)
+{
+	return 0 == k ? v.x : (1 == k ? v.y : (2 == k ? v.z : v.w));
+}
+
+/// Row (A side) / column (B side) a thread owns, relative to the warp tile.
+/// k-contiguous operands interleave (see file header), the others block by 4.
+template <bool AK>
+__device__ __forceinline__ int row_of (int tm, int i)
+{
+	return AK ? tm + 8 * i : tm * 4 + (i & 3) + 32 * (i >> 2);
+}
+
+template <bool BKC>
+__device__ __forceinline__ int col_of (int tn, int j)
+{
+	return BKC ? tn * 2 + (j & 1) + 8 * (j >> 1) :
+		tn * 4 + (j & 3) + 16 * (j >> 2);
+}
+
+/// Operand fragments of one thread, double-buffered so the loads of the next
+/// k (or k-group) are in flight while the current one feeds the FFMAs.
+///   KC (k-contiguous, swizzled [row][k] tile): 8 rows x 4 consecutive k per
+///       k-group as float4; the next group's 8 vectors are fetched two per k
+///   otherwise ([k][row] tile): 8 rows of one k as two float4 per k
+template <bool KC>
+struct Frag
+{
+	float4 v[2][KC ? 8 : 2];
+};
+
+template <bool AK, bool BKC>
+__global__ void __launch_bounds__(THREADS, 1)
+sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
+	const __grid_constant__ CUtensorMap map_b,
+	const __grid_constant__ SgemmArgs args)
+{
+	extern __shared__ __align__(1024) unsigned char smem_raw[];
+	// 128-byte swizzled tiles must start on a 1024-byte boundary
+	// (offset arithmetic on the __shared__ symbol keeps the address space,
+	// so tile reads compile to LDS rather than generic LD)
+	unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+	float* tiles_a = (float*) smem;
+	float* tiles_b = tiles_a + STAGES * A_STAGE_FLOATS;
+	uint64_t* full = (uint64_t*) (smem + (size_t) STAGES * STAGE_BYTES + TAIL_PAD);
+	uint64_t* empty = full + STAGES;
+
+	// tile order: walk GROUP tile-rows per tile-column so the CTAs in flight
+	// share their A panels and B panels in L2
+	constexpr uint32_t GROUP = 16;
+	uint32_t bid = blockIdx.x;
+	uint32_t per_group = GROUP * args.tiles_n;
+	uint32_t first_m = (bid / per_group) * GROUP;
+	uint32_t gsize = min(args.tiles_m - first_m, GROUP);
+	uint32_t tile_m = first_m + (bid % per_group) % gsize;
+	uint32_t tile_n = (bid % per_group) / gsize;
+	uint32_t ktiles = (args.K + BK - 1) / BK;
+
+	int warp = threadIdx.x >> 5;
+	int lane = threadIdx.x & 31;
+
+	// one elected lane moves both operand tiles of k-tile `kt` with TMA
+	auto issue = [&] (uint32_t kt)
+	{
+		uint32_t s = kt % STAGES;
+		mbar_expect_tx(&full[s], STAGE_BYTES);
+		int k0 = (int) (kt * BK);
+		if (AK)
+		{
+			tma_load_2d(tiles_a + s * A_STAGE_FLOATS, &map_a, &full[s],
+				k0, (int) (tile_m * BM));
+		}
+		else
+		{
+			tma_load_2d(tiles_a + s * A_STAGE_FLOATS, &map_a, &full[s],
+				(int) (tile_m * BM), k0);
+		}
+		if (BKC)
+		{
+			tma_load_2d(tiles_b + s * B_STAGE_FLOATS, &map_b, &full[s],
+				k0, (int) (tile_n * BN));
+		}
+		else
+		{
+			tma_load_2d(tiles_b + s * B_STAGE_FLOATS, &map_b, &full[s],
+				(int) (tile_n * BN), k0);
+		}
+	};
+
+	if (0 == threadIdx.x)
+	{
+		for (int s = 0; s < STAGES; ++s)
+		{
+			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], WARPS);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
+		asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b) : "memory");
+		for (uint32_t kt = 0; kt < LEAD && kt < ktiles; ++kt)
+		{
+			issue(kt);
+		}
+	}
+	__syncthreads();
+
+	int wm = warp >> 2;   // 0..1
+	int wn = warp & 3;    // 0..3
+	int tm = lane >> 2;   // 0..7
+	int tn = lane & 3;    // 0..3
+	float acc[8][8];
+#pragma unroll
+	for (int i = 0; i < 8; ++i)
+	{
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+		{
+			acc[i][j] = 0.0f;
+		}
+	}
+
+	// thread-constant parts of the fragment addresses (in float4 units)
+	//   KC : row * 8 + (kg ^ (row & 7)), rows r0 + 8i resp. cols c(j)
+	//   else: k * 32 + row / 4
+	const int a_row4 = AK ? (wm * 64 + tm) * (BK / 4) : (wm * 64 + tm * 4) / 4;
+	const int b_row4 = BKC ? 0 : (wn * 32 + tn * 4) / 4;
+	const int a_key = tm;
+	int b_col[8];
+	if (BKC)
+	{
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+		{
+			b_col[j] = wn * 32 + col_of<true>(tn, j);
+		}
+	}
+
+	for (uint32_t kt = 0; kt < ktiles; ++kt)
+	{
+		uint32_t s = kt % STAGES;
+		// the producer duty rotates over the warps: k-tile kt + LEAD goes
+		// into the stage every warp released STAGES - LEAD iterations ago
+		if ((int) (kt % WARPS) == warp && 0 == lane && kt + LEAD < ktiles)
+		{
+			if (kt + LEAD >= STAGES)
+			{
+				uint32_t prev = kt + LEAD - STAGES;
+				mbar_wait(&empty[prev % STAGES], (prev / STAGES) & 1);
+			}
+			issue(kt + LEAD);
+		}
+		__syncwarp();
+		mbar_wait(&full[s], (kt / STAGES) & 1);
+		const float4* As4 = (const float4*) (tiles_a + s * A_STAGE_FLOATS);
+		const float4* Bs4 = (const float4*) (tiles_b + s * B_STAGE_FLOATS);
+
+		Frag<AK> fa;
+		Frag<BKC> fb;
+		// ---- prologue: fragments of k-group 0 / k 0 ----
+		if (AK)
+		{
+#pragma unroll
+			for (int i = 0; i < 8; ++i)
+			{
+				fa.v[0][i] = As4[a_row4 + i * 8 * (BK / 4) + (0 ^ a_key)];
+			}
+		}
+		else
+		{
+			fa.v[0][0] = As4[a_row4];
+			fa.v[0][1] = As4[a_row4 + 8];
+		}
+		if (BKC)
+		{
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+			{
+				fb.v[0][j] = Bs4[b_col[j] * (BK / 4) + (0 ^ (b_col[j] & 7))];
+			}
+		}
+		else
+		{
+			fb.v[0][0] = Bs4[b_row4];
+			fb.v[0][1] = Bs4[b_row4 + 4];
+		}
+
+#pragma unroll 1
+		for (int kgp = 0; kgp < BK / 8; ++kgp)
+		{
+#pragma unroll
+			for (int h = 0; h < 2; ++h)
+			{
+				const int kg = 2 * kgp + h;
+				// (the prefetch of the last step reads past the stage: unused)
+				const bool more_kg = true;
+#pragma unroll
+				for (int kk = 0; kk < 4; ++kk)
+				{
+					const int k = kg * 4 + kk;
+					const bool more_k = (kk < 3) || more_kg;
+					// ---- prefetch ----
+					if (AK)
+					{
+						if (more_kg)
+						{
+							int chunk = (kg + 1) ^ a_key;
+							fa.v[h ^ 1][2 * kk] = As4[a_row4 +
+								(2 * kk) * 8 * (BK / 4) + chunk];
+							fa.v[h ^ 1][2 * kk + 1] = As4[a_row4 +
+								(2 * kk + 1) * 8 * (BK / 4) + chunk];
+						}
+					}
+					else if (more_k)
+					{
+						fa.v[(kk + 1) & 1][0] = As4[(k + 1) * (BM / 4) + a_row4];
+						fa.v[(kk + 1) & 1][1] = As4[(k + 1) * (BM / 4) + a_row4 + 8];
+					}
+					if (BKC)
+					{
+						if (more_kg)
+						{
+#pragma unroll
+							for (int q = 0; q < 2; ++q)
+							{
+								int j = 2 * kk + q;
+								fb.v[h ^ 1][j] = Bs4[b_col[j] * (BK / 4) +
+									((kg + 1) ^ (b_col[j] & 7))];
+							}
+						}
+					}
+					else if (more_k)
+					{
+						fb.v[(kk + 1) & 1][0] = Bs4[(k + 1) * (BN / 4) + b_row4];
+						fb.v[(kk + 1) & 1][1] = Bs4[(k + 1) * (BN / 4) + b_row4 + 4];
+					}
+					// ---- this k ----
+					float a[8];
+					float b[8];
+					if (AK)
+					{
+#pragma unroll
+						for (int i = 0; i < 8; ++i)
+						{
+							a[i] = comp(fa.v[h][i], kk);
+						}
+					}
+					else
+					{
+						float4 lo = fa.v[kk & 1][0];
+						float4 hi = fa.v[kk & 1][1];
+						a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w;
+						a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+					}
+					if (BKC)
+					{
+#pragma unroll
+						for (int j = 0; j < 8; ++j)
+						{
+							b[j] = comp(fb.v[h][j], kk);
+						}
+					}
+					else
+					{
+						float4 lo = fb.v[kk & 1][0];
+						float4 hi = fb.v[kk & 1][1];
+						b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = lo.w;
+						b[4] = hi.x; b[5] = hi.y; b[6] = hi.z; b[7] = hi.w;
+					}
+#pragma unroll
+					for (int i = 0; i < 8; ++i)
+					{
+#pragma unroll
+						for (int j = 0; j < 8; ++j)
+						{
+							acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+						}
+					}
+				}
+			}
+		}
+		__syncwarp();
+		if (0 == lane)
+		{
+			mbar_arrive(&empty[s]);
+		}
+	}
+
+	// ---- epilogue: registers -> C ----
+	uint32_t m_base = tile_m * BM + wm * 64;
+	uint32_t n_base = tile_n * BN + wn * 32;
+#pragma unroll
+	for (int i = 0; i < 8; ++i)
+	{
+		uint32_t m = m_base + row_of<AK>(tm, i);
+		if (m >= args.M)
+		{
+			continue;
+		}
+		float* crow = args.C + (int64_t) m * args.c_rs;
+		if (BKC)
+		{
+#pragma unroll
+			for (int j = 0; j < 8; j += 2)
+			{
+				uint32_t n = n_base + col_of<true>(tn, j);
+				if (args.vec_store && n + 1 < args.N)
+				{
+					*(float2*) (crow + n) = make_float2(acc[i][j], acc[i][j + 1]);
+				}
+				else
+				{
+					if (n < args.N) { crow[n] = acc[i][j]; }
+					if (n + 1 < args.N) { crow[n + 1] = acc[i][j + 1]; }
+				}
+			}
+		}
+		else
+		{
+#pragma unroll
+			for (int j = 0; j < 8; j += 4)
+			{
+				uint32_t n = n_base + col_of<false>(tn, j);
+				if (args.vec_store && n + 3 < args.N)
+				{
+					*(float4*) (crow + n) = make_float4(acc[i][j], acc[i][j + 1],
+						acc[i][j + 2], acc[i][j + 3]);
+				}
+				else
+				{
+#pragma unroll
+					for (int e = 0; e < 4; ++e)
+					{
+						if (n + e < args.N) { crow[n + e] = acc[i][j + e]; }
+					}
+				}
+			}
+		}
+	}
+}
+
+// ---- host side -----------------------------------------------------------------
+
+using EncodeFn = CUresult (*) (CUtensorMap*, CUtensorMapDataType, cuuint32_t,
+	void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+	const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+	CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn tensor_map_encoder (void)
+{
+	static EncodeFn fn = nullptr;
+	static bool tried = false;
+	if (false == tried)
+	{
+		tried = true;
+		void* sym = nullptr;
+		cudaDriverEntryPointQueryResult status;
+		if (cudaSuccess == cudaGetDriverEntryPoint("cuTensorMapEncodeTiled",
+			&sym, cudaEnableDefault, &status) &&
+			cudaDriverEntryPointSuccess == status)
+		{
+			fn = (EncodeFn) sym;
+		}
+		cudaGetLastError();
+	}
+	return fn;
+}
+
+/// 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows of
+/// `outer_stride` elements; box = box_inner x box_outer
+bool make_map (CUtensorMap& map, const float* base, uint64_t inner,
+	uint64_t outer, int64_t outer_stride, uint32_t box_inner,
+	uint32_t box_outer, bool swizzle)
+{
+	EncodeFn encode = tensor_map_encoder();
+	if (nullptr == encode)
+	{
+		return false;
+	}
+	cuuint64_t dims[2] = {inner, outer};
+	cuuint64_t strides[1] = {(cuuint64_t) outer_stride * sizeof(float)};
+	cuuint32_t box[2] = {box_inner, box_outer};
+	cuuint32_t estrides[2] = {1, 1};
+	CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+		(void*) base, dims, strides, box, estrides,
+		CU_TENSOR_MAP_INTERLEAVE_NONE,
+		swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+		CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return CUDA_SUCCESS == rc;
+}
+
+bool tma_operand_ok (const float* base, int64_t lead)
+{
+	return 0 == ((uintptr_t) base & 15u) && lead > 0 && 0 == lead % 4 &&
+		lead < (1ll << 38);
+}
+
+template <bool AK, bool BKC>
+int launch_variant (llo_cuda_ctx* ctx, const CUtensorMap& ma,
+	const CUtensorMap& mb, const SgemmArgs& args)
+{
+	static bool configured = false;
+	if (false == configured)
+	{
+		LLO_CUDA_TRY(cudaFuncSetAttribute(sgemm_tma_kernel<AK,BKC>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM_BYTES));
+		configured = true;
+	}
+	uint64_t blocks = (uint64_t) args.tiles_m * args.tiles_n;
+	sgemm_tma_kernel<AK,BKC><<<(unsigned) blocks, THREADS, SMEM_BYTES,
+		ctx->stream>>>(ma, mb, args);
+	return launched(ctx, "sgemm_tma_kernel");
+}
+
+}
+
+int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p0, float* C,
+	const float* A, const float* B, int precision, bool& handled)
 {
 	handled = false;
-	return LLO_OK;
+	if (LLO_GEMM_EXACT != precision)
+	{
+		return LLO_OK; // 3xTF32 not wired yet: the exact path is always valid
+	}
+	GemmParams p = p0;
+	// C must have contiguous columns; a column-major C is the row-major C^T
+	// of the transposed product B^T A^T
+	if (1 != p.c_cs && p.N > 1)
+	{
+		if (1 != p.c_rs && p.M > 1)
+		{
+			return LLO_OK;
+		}
+		std::swap(p.M, p.N);
+		std::swap(A, B);
+		int64_t a_rs = p.b_cs, a_cs = p.b_rs, b_rs = p.a_cs, b_cs = p.a_rs;
+		p.a_rs = a_rs; p.a_cs = a_cs; p.b_rs = b_rs; p.b_cs = b_cs;
+		std::swap(p.c_rs, p.c_cs);
+	}
+	if (p.M < 32 || p.N < 32 || p.K < 32 ||
+		p.M >= (1ull << 31) || p.N >= (1ull << 31) || p.K >= (1ull << 31))
+	{
+		return LLO_OK; // skinny / tiny / huge problems take the generic kernel
+	}
+	bool ak = (1 == p.a_cs);
+	bool bk = (1 == p.b_rs);
+	if ((false == ak && 1 != p.a_rs) || (false == bk && 1 != p.b_cs))
+	{
+		return LLO_OK;
+	}
+	int64_t lead_a = ak ? p.a_rs : p.a_cs;
+	int64_t lead_b = bk ? p.b_cs : p.b_rs;
+	if (false == tma_operand_ok(A, lead_a) || false == tma_operand_ok(B, lead_b))
+	{
+		return LLO_OK;
+	}
+	CUtensorMap ma, mb;
+	bool ok = ak ?
+		make_map(ma, A, p.K, p.M, lead_a, BK, BM, true) :
+		make_map(ma, A, p.M, p.K, lead_a, BM, BK, false);
+	ok = ok && (bk ?
+		make_map(mb, B, p.K, p.N, lead_b, BK, BN, true) :
+		make_map(mb, B, p.N, p.K, lead_b, BN, BK, false));
+	if (false == ok)
+	{
+		return LLO_OK;
+	}
+	SgemmArgs args;
+	args.C = C;
+	args.c_rs = p.c_rs;
+	args.M = (uint32_t) p.M;
+	args.N = (uint32_t) p.N;
+	args.K = (uint32_t) p.K;
+	args.tiles_m = (uint32_t) ((p.M + BM - 1) / BM);
+	args.tiles_n = (uint32_t) ((p.N + BN - 1) / BN);
+	int64_t need = bk ? 2 : 4;
+	args.vec_store = (0 == ((uintptr_t) C & (uintptr_t) (need * 4 - 1)) &&
+		0 == p.c_rs % need) ? 1 : 0;
+	if ((uint64_t) args.tiles_m * args.tiles_n >= 0x7fffffffull)
+	{
+		return LLO_OK;
+	}
+	handled = true;
+	if (ak)
+	{
+		return bk ? launch_variant<true,true>(ctx, ma, mb, args) :
+			launch_variant<true,false>(ctx, ma, mb, args);
+	}
+	return bk ? launch_variant<false,true>(ctx, ma, mb, args) :
+		launch_variant<false,false>(ctx, ma, mb, args);
 }
 
 }

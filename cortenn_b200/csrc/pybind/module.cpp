@@ -338,9 +338,12 @@ PYBIND11_MODULE(_C, m)
 			});
 	llo_m.def("evaluate_device", [](T tens, py::dtype dtype)
 		{
+			age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);
 			pyllo::DeviceResult out;
-			py::gil_scoped_release release;
-			out.data_ = llo::eval_device(tens, pyllo::eval_dtype(dtype));
+			{
+				py::gil_scoped_release release;
+				out.data_ = llo::eval_device(tens, ctype);
+			}
 			return out;
 		}, py::arg("tens"), py::arg("dtype") = py::dtype::of<double>());
 	llo_m.def("available", []() { return llo::device::available(); });
