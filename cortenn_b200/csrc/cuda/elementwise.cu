@@ -11,24 +11,25 @@
 namespace llo_cuda
 {
 
-// ---- flat launch: one chunk per thread ---------------------------------------
+// ---- flat launch: 256 threads x V consecutive outputs per CTA -------------------
 
 template <typename T>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(VM_THREADS, 4)
 vm_flat_kernel (const __grid_constant__ VmParams p)
 {
-	constexpr int VEC = VmVec<T>::value;
-	uint64_t base = ((uint64_t) blockIdx.x * 256 + threadIdx.x) * VEC;
-	if (base >= p.n)
+	using G = VmGeom<T>;
+	extern __shared__ __align__(16) unsigned char vm_smem[];
+	uint64_t base = (uint64_t) blockIdx.x * (VM_THREADS * G::V);
+	FlatLoader<T> loader = {p, base, base + VM_THREADS * G::V <= p.n};
+	T acc[G::V];
+	vm_exec<T>(acc, p, loader, reinterpret_cast<T*>(vm_smem));
+	T* out = static_cast<T*>(p.out) + loader.first(0);
+#pragma unroll
+	for (int u = 0; u < G::U; ++u)
 	{
-		return;
+		store_chunk<T,G::E>(out + u * VM_THREADS * G::E, acc + u * G::E,
+			p.out_vec_ok, loader.valid(u));
 	}
-	uint64_t left = p.n - base;
-	int valid = left < (uint64_t) VEC ? (int) left : VEC;
-	FlatLoader<T,VEC> loader = {p, base, valid};
-	T acc[VEC];
-	vm_run<T,VEC>(acc, p, loader);
-	store_run<T,VEC>(static_cast<T*>(p.out) + base, acc, p.out_vec_ok, valid);
 }
 
 // ---- tile launch: transposed inputs staged through shared memory ---------------
@@ -49,51 +50,67 @@ __device__ __forceinline__ int64_t rest_offset (const VmParams& p,
 	return off;
 }
 
-template <typename T, int VEC>
+/// Input access of the tile launch.  Chunk u of thread t is row
+/// t / 16 + 16 u of the tile, columns (t % 16) * E .. +E
+template <typename T>
 struct TileLoader
 {
+	using G = VmGeom<T>;
+
 	const VmParams& p;
-	const T* tiles;          // [slot][VM_TILEP][pitch]
-	uint32_t c0;             // coordinates of this thread's chunk in the plane
-	uint32_t c1;
+	const T* tiles;          // [slot][TILEP][PITCH]
+	uint32_t c0;             // dim-0 coordinate of this thread's chunks
+	uint32_t c1;             // staged-dim coordinate of chunk 0
+	uint32_t dim1;
 	uint32_t brest;
-	int col;                 // chunk position inside the tile
-	int row;
-	int valid;
+	int valid0;              // elements of a chunk inside dim 0
 
-	static constexpr int PITCH = 8 * VEC + 1;
+	__device__ __forceinline__ int valid (int u) const
+	{
+		return (c1 + 16 * u < dim1) ? valid0 : 0;
+	}
 
-	__device__ __forceinline__ void load (T (&dst)[VEC], int k) const
+	__device__ __forceinline__ void load (T (&x)[G::V], int k) const
 	{
 		const VmInput& in = p.in[k];
 		if (VM_IN_TILE == in.mode)
 		{
-			const T* src = tiles +
-				((size_t) in.vec_ok * VM_TILEP + row) * PITCH + col;
+			const T* src = tiles + ((size_t) in.vec_ok * G::TILEP +
+				(threadIdx.x >> 4)) * G::PITCH + (threadIdx.x & 15) * G::E;
 #pragma unroll
-			for (int e = 0; e < VEC; ++e)
+			for (int u = 0; u < G::U; ++u)
 			{
-				dst[e] = src[e];
+#pragma unroll
+				for (int e = 0; e < G::E; ++e)
+				{
+					x[u * G::E + e] = src[u * 16 * G::PITCH + e];
+				}
 			}
 		}
 		else
 		{
 			int64_t off = in.offset + (int64_t) c0 * in.stride[0] +
 				(int64_t) c1 * in.stride[1] + rest_offset(p, in.stride, brest);
-			load_strided_run<T,VEC>(dst, in, off, valid);
+#pragma unroll
+			for (int u = 0; u < G::U; ++u)
+			{
+				int ok = valid(u);
+				load_strided_chunk<T,G::E>(x + u * G::E, in,
+					ok > 0 ? off + (int64_t) (16 * u) * in.stride[1] : in.offset,
+					ok);
+			}
 		}
 	}
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(VM_THREADS, 3)
 vm_tile_kernel (const __grid_constant__ VmParams p)
 {
-	constexpr int VEC = VmVec<T>::value;
-	constexpr int TILE0 = 8 * VEC;
-	constexpr int PITCH = TILE0 + 1;
-	extern __shared__ __align__(16) unsigned char tile_raw[];
-	T* tiles = reinterpret_cast<T*>(tile_raw);
+	using G = VmGeom<T>;
+	extern __shared__ __align__(16) unsigned char vm_smem[];
+	T* tiles = reinterpret_cast<T*>(vm_smem);
+	T* spill = tiles + (size_t) VM_MAX_TILE_INPUTS * G::TILEP * G::PITCH;
 
 	// block -> (tile along dim 0, tile along dim 1, every other dim)
 	uint32_t b = blockIdx.x;
@@ -101,8 +118,8 @@ vm_tile_kernel (const __grid_constant__ VmParams p)
 	b /= p.tiles0;
 	uint32_t tp = b % p.tilesp;
 	uint32_t brest = b / p.tilesp;
-	uint32_t o0 = t0 * TILE0;
-	uint32_t o1 = tp * VM_TILEP;
+	uint32_t o0 = t0 * G::TILE0;
+	uint32_t o1 = tp * G::TILEP;
 	uint32_t dim0 = (uint32_t) p.dims[0];
 	uint32_t dim1 = (uint32_t) p.dims[1];
 
@@ -117,18 +134,17 @@ vm_tile_kernel (const __grid_constant__ VmParams p)
 		const T* data = static_cast<const T*>(in.data);
 		int64_t origin = in.offset + (int64_t) o0 * in.stride[0] +
 			(int64_t) o1 * in.stride[1] + rest_offset(p, in.stride, brest);
-		T* tile = tiles + (size_t) in.vec_ok * VM_TILEP * PITCH;
-		// a warp covers 32 consecutive elements of the input's contiguous
-		// direction; 256 threads sweep the TILE0 x TILEP tile in
-		// TILE0 * TILEP / 256 steps, all loads issued before any is used
-		constexpr int STEPS = TILE0 * VM_TILEP / 256;
-		T v[STEPS];
+		T* tile = tiles + (size_t) in.vec_ok * G::TILEP * G::PITCH;
+		// a warp covers consecutive elements of the input's contiguous
+		// direction; 256 threads sweep the TILE0 x TILEP tile in V steps,
+		// all loads issued before any is used
+		T v[G::V];
 #pragma unroll
-		for (int j = 0; j < STEPS; ++j)
+		for (int j = 0; j < G::V; ++j)
 		{
-			int e = threadIdx.x + 256 * j;
-			int lp = e % VM_TILEP;
-			int r0 = e / VM_TILEP;
+			int e = threadIdx.x + VM_THREADS * j;
+			int lp = e % G::TILEP;
+			int r0 = e / G::TILEP;
 			v[j] = T();
 			if (o1 + lp < dim1 && o0 + r0 < dim0)
 			{
@@ -136,35 +152,36 @@ vm_tile_kernel (const __grid_constant__ VmParams p)
 			}
 		}
 #pragma unroll
-		for (int j = 0; j < STEPS; ++j)
+		for (int j = 0; j < G::V; ++j)
 		{
-			int e = threadIdx.x + 256 * j;
-			tile[(e % VM_TILEP) * PITCH + e / VM_TILEP] = v[j];
+			int e = threadIdx.x + VM_THREADS * j;
+			tile[(e % G::TILEP) * G::PITCH + e / G::TILEP] = v[j];
 		}
 	}
 	__syncthreads();
 
-	// 8 chunk columns x 32 rows per pass, TILEP / 32 passes
-#pragma unroll 1
-	for (int pass = 0; pass < VM_TILEP / 32; ++pass)
+	TileLoader<T> loader = {p, tiles, 0, 0, dim1, brest, 0};
+	loader.c0 = o0 + (threadIdx.x & 15) * G::E;
+	loader.c1 = o1 + (threadIdx.x >> 4);
+	if (loader.c0 < dim0)
 	{
-		TileLoader<T,VEC> loader = {p, tiles, 0, 0, brest, 0, 0, 0};
-		loader.col = (threadIdx.x & 7) * VEC;
-		loader.row = (threadIdx.x >> 3) + 32 * pass;
-		loader.c0 = o0 + loader.col;
-		loader.c1 = o1 + loader.row;
-		if (loader.c0 >= dim0 || loader.c1 >= dim1)
-		{
-			continue;
-		}
 		uint32_t left = dim0 - loader.c0;
-		loader.valid = left < (uint32_t) VEC ? (int) left : VEC;
-		T acc[VEC];
-		vm_run<T,VEC>(acc, p, loader);
-		T* out = static_cast<T*>(p.out) + (int64_t) loader.c0 * p.out_stride[0] +
-			(int64_t) loader.c1 * p.out_stride[1] +
-			rest_offset(p, p.out_stride, brest);
-		store_run<T,VEC>(out, acc, p.out_vec_ok, loader.valid);
+		loader.valid0 = left < (uint32_t) G::E ? (int) left : G::E;
+	}
+	T acc[G::V];
+	vm_exec<T>(acc, p, loader, spill);
+	T* out = static_cast<T*>(p.out) + (int64_t) loader.c0 * p.out_stride[0] +
+		(int64_t) loader.c1 * p.out_stride[1] +
+		rest_offset(p, p.out_stride, brest);
+#pragma unroll
+	for (int u = 0; u < G::U; ++u)
+	{
+		int ok = loader.valid(u);
+		if (ok > 0)
+		{
+			store_chunk<T,G::E>(out + (int64_t) (16 * u) * p.out_stride[1],
+				acc + u * G::E, p.out_vec_ok, ok);
+		}
 	}
 }
 
@@ -173,9 +190,126 @@ static bool aligned16 (const void* ptr, int64_t elem_offset, size_t esize)
 	return 0 == (((uintptr_t) ptr + (uintptr_t) (elem_offset * (int64_t) esize)) & 15u);
 }
 
-/// Validate the public stack program and resolve every instruction's stack
-/// slot (VmOp::sel)
-static int vm_encode (VmOp* code, int dtype, int ninputs, int nconsts,
+// ---- stack program -> accumulator program --------------------------------------
+
+namespace
+{
+
+struct Expr
+{
+	int kind;   // 0 input, 1 constant, 2 unary, 3 binary
+	int op;     // public opcode
+	int arg;    // input / constant number
+	int lhs;
+	int rhs;
+	int need;   // spill levels needed to evaluate
+};
+
+struct Encoder
+{
+	Expr nodes[LLO_VM_MAX_INSNS];
+	VmOp* code;
+	int ncode = 0;
+	int depth = 0;
+	int peak = 0;
+	bool overflow = false;
+
+	bool leaf (int n) const { return nodes[n].kind < 2; }
+
+	uint8_t source (int n) const
+	{
+		return (uint8_t) (((0 == nodes[n].kind ? VM_SRC_IN : VM_SRC_CONST) << 4) |
+			nodes[n].arg);
+	}
+
+	void emit (int sel, uint8_t arg)
+	{
+		if (ncode >= VM_MAX_CODE)
+		{
+			overflow = true;
+			return;
+		}
+		code[ncode].sel = (uint8_t) sel;
+		code[ncode].arg = arg;
+		++ncode;
+	}
+
+	static int unary_sel (int op)
+	{
+		switch (op)
+		{
+			case LLO_OP_ABS: return VM_S_ABS;
+			case LLO_OP_NEG: return VM_S_NEG;
+			case LLO_OP_ROUND: return VM_S_ROUND;
+			case LLO_OP_SIN: return VM_S_SIN;
+			case LLO_OP_COS: return VM_S_COS;
+			case LLO_OP_TAN: return VM_S_TAN;
+			case LLO_OP_EXP: return VM_S_EXP;
+			case LLO_OP_LOG: return VM_S_LOG;
+			default: return VM_S_SQRT;
+		}
+	}
+
+	/// acc <- op(acc, x), or op(x, acc) when reversed
+	static int binary_sel (int op, bool reversed)
+	{
+		switch (op)
+		{
+			case LLO_OP_SUM: return VM_S_SUM;
+			case LLO_OP_PROD: return VM_S_PROD;
+			case LLO_OP_EQ: return VM_S_EQ;
+			case LLO_OP_NEQ: return VM_S_NEQ;
+			case LLO_OP_SUB: return reversed ? VM_S_RSUB : VM_S_SUB;
+			case LLO_OP_MIN: return reversed ? VM_S_RMIN : VM_S_MIN;
+			case LLO_OP_MAX: return reversed ? VM_S_RMAX : VM_S_MAX;
+			case LLO_OP_LT: return reversed ? VM_S_GT : VM_S_LT;
+			case LLO_OP_GT: return reversed ? VM_S_LT : VM_S_GT;
+			case LLO_OP_DIV: return reversed ? VM_S_RDIV : VM_S_DIV;
+			default: return reversed ? VM_S_RPOW : VM_S_POW;
+		}
+	}
+
+	void gen (int n)
+	{
+		const Expr& x = nodes[n];
+		if (x.kind < 2)
+		{
+			emit(VM_S_SET, source(n));
+		}
+		else if (2 == x.kind)
+		{
+			gen(x.lhs);
+			emit(unary_sel(x.op), 0);
+		}
+		else if (leaf(x.rhs))
+		{
+			gen(x.lhs);
+			emit(binary_sel(x.op, false), source(x.rhs));
+		}
+		else if (leaf(x.lhs))
+		{
+			gen(x.rhs);
+			emit(binary_sel(x.op, true), source(x.lhs));
+		}
+		else
+		{
+			// both operands are sub-expressions: the hungrier one first
+			bool lhs_first = nodes[x.lhs].need >= nodes[x.rhs].need;
+			gen(lhs_first ? x.lhs : x.rhs);
+			emit(VM_S_PUSH, 0);
+			++depth;
+			peak = depth > peak ? depth : peak;
+			gen(lhs_first ? x.rhs : x.lhs);
+			--depth;
+			emit(binary_sel(x.op, lhs_first), (uint8_t) (VM_SRC_POP << 4));
+		}
+	}
+};
+
+}
+
+/// Validate the public stack program and compile it to accumulator form
+static int vm_encode (VmParams& p, int dtype, int ninputs, int nconsts,
 	const llo_cuda_insn* program, int ninsns)
 {
 	if (ninputs < 0 || ninputs > LLO_VM_MAX_INPUTS ||
@@ -186,12 +320,16 @@ static int vm_encode (VmOp* code, int dtype, int ninputs, int nconsts,
 			"(%d inputs, %d consts, %d instructions)",
 			ninputs, nconsts, ninsns);
 	}
+	Encoder enc;
+	enc.code = p.code;
+	int stack[LLO_VM_MAX_DEPTH];
 	int depth = 0;
 	for (int pc = 0; pc < ninsns; ++pc)
 	{
 		int op = program[pc].op;
 		int arg = program[pc].arg;
-		int sel = -1;
+		Expr& node = enc.nodes[pc];
+		node = Expr{0, op, arg, -1, -1, 0};
 		if (LLO_VM_LOAD == op || LLO_VM_CONST == op)
 		{
 			int limit = LLO_VM_LOAD == op ? ninputs : nconsts;
@@ -205,8 +343,8 @@ static int vm_encode (VmOp* code, int dtype, int ninputs, int nconsts,
 				return fail(LLO_ERR_FATAL, "program needs more than %d stack "
 					"slots", LLO_VM_MAX_DEPTH);
 			}
-			sel = (LLO_VM_LOAD == op ? VM_SEL_LOAD : VM_SEL_CONST) + depth;
-			++depth;
+			node.kind = LLO_VM_LOAD == op ? 0 : 1;
+			stack[depth++] = pc;
 		}
 		else if (is_unary_op(op))
 		{
@@ -220,19 +358,10 @@ static int vm_encode (VmOp* code, int dtype, int ninputs, int nconsts,
 				return fail(LLO_ERR_UNSUPPORTED_TYPED_OP,
 					"NEG is not defined for %s", dtype_name(dtype));
 			}
-			int slot = depth - 1;
-			switch (op)
-			{
-				case LLO_OP_ABS: sel = VM_SEL_ABS + slot; break;
-				case LLO_OP_NEG: sel = VM_SEL_NEG + slot; break;
-				case LLO_OP_ROUND: sel = VM_SEL_ROUND + slot; break;
-				case LLO_OP_SIN: sel = VM_SEL_HEAVY + 4 * VM_H_SIN + slot; break;
-				case LLO_OP_COS: sel = VM_SEL_HEAVY + 4 * VM_H_COS + slot; break;
-				case LLO_OP_TAN: sel = VM_SEL_HEAVY + 4 * VM_H_TAN + slot; break;
-				case LLO_OP_EXP: sel = VM_SEL_HEAVY + 4 * VM_H_EXP + slot; break;
-				case LLO_OP_LOG: sel = VM_SEL_HEAVY + 4 * VM_H_LOG + slot; break;
-				default: sel = VM_SEL_HEAVY + 4 * VM_H_SQRT + slot; break;
-			}
+			node.kind = 2;
+			node.lhs = stack[depth - 1];
+			node.need = enc.nodes[node.lhs].need;
+			stack[depth - 1] = pc;
 		}
 		else if (is_binary_op(op) || is_nnary_op(op))
 		{
@@ -240,40 +369,47 @@ static int vm_encode (VmOp* code, int dtype, int ninputs, int nconsts,
 			{
 				return fail(LLO_ERR_FATAL, "program underflows its stack");
 			}
-			int slot = depth - 2;
-			switch (op)
+			node.kind = 3;
+			node.lhs = stack[depth - 2];
+			node.rhs = stack[depth - 1];
+			int nl = enc.nodes[node.lhs].need;
+			int nr = enc.nodes[node.rhs].need;
+			if (enc.leaf(node.lhs) || enc.leaf(node.rhs))
 			{
-				case LLO_OP_SUM: sel = VM_SEL_SUM + slot; break;
-				case LLO_OP_SUB: sel = VM_SEL_SUB + slot; break;
-				case LLO_OP_PROD: sel = VM_SEL_PROD + slot; break;
-				case LLO_OP_MIN: sel = VM_SEL_MIN + slot; break;
-				case LLO_OP_MAX: sel = VM_SEL_MAX + slot; break;
-				case LLO_OP_EQ: sel = VM_SEL_EQ + slot; break;
-				case LLO_OP_NEQ: sel = VM_SEL_NEQ + slot; break;
-				case LLO_OP_LT: sel = VM_SEL_LT + slot; break;
-				case LLO_OP_GT: sel = VM_SEL_GT + slot; break;
-				case LLO_OP_POW: sel = VM_SEL_HEAVY + 4 * VM_H_POW + slot; break;
-				default: sel = VM_SEL_HEAVY + 4 * VM_H_DIV + slot; break;
+				node.need = nl > nr ? nl : nr;
+			}
+			else
+			{
+				int hi = nl >= nr ? nl : nr;
+				int lo = nl >= nr ? nr : nl;
+				node.need = hi > lo + 1 ? hi : lo + 1;
 			}
 			--depth;
+			stack[depth - 1] = pc;
 		}
 		else
 		{
 			return fail(LLO_ERR_FATAL, "opcode %d is not elementwise", op);
 		}
-		code[pc].sel = (uint8_t) sel;
-		code[pc].arg = (uint8_t) arg;
 	}
 	if (1 != depth)
 	{
 		return fail(LLO_ERR_FATAL, "program leaves %d values", depth);
 	}
+	enc.gen(stack[0]);
+	if (enc.overflow || enc.peak > VM_MAX_SPILL)
+	{
+		return fail(LLO_ERR_FATAL, "elementwise program too large for the "
+			"engine (%d instructions, %d spill levels)", enc.ncode, enc.peak);
+	}
+	p.ninsns = enc.ncode;
+	p.spill_depth = enc.peak;
 	return LLO_OK;
 }
 
 int vm_prepare (VmParams& p, int dtype, const uint64_t outshape[LLO_RANK],
 	const VmInput* inputs, int ninputs, const void* consts, int nconsts,
-	const llo_cuda_insn* program, int ninsns, int vec)
+	const llo_cuda_insn* program, int ninsns, int chunk, int span)
 {
 	size_t esize = dtype_size(dtype);
 	if (0 == esize)
@@ -281,9 +417,8 @@ int vm_prepare (VmParams& p, int dtype, const uint64_t outshape[LLO_RANK],
 		return fail(LLO_ERR_FATAL, "executing bad type %d", dtype);
 	}
 	std::memset(&p, 0, sizeof(p));
-	LLO_TRY(vm_encode(p.code, dtype, ninputs, nconsts, program, ninsns));
+	LLO_TRY(vm_encode(p, dtype, ninputs, nconsts, program, ninsns));
 	p.n = n_elems(outshape);
-	p.ninsns = ninsns;
 	p.ninputs = ninputs;
 	for (int c = 0; c < nconsts; ++c)
 	{
@@ -352,7 +487,8 @@ int vm_prepare (VmParams& p, int dtype, const uint64_t outshape[LLO_RANK],
 		p.out_stride[d] = dense;
 		dense *= (int64_t) dims[d];
 	}
-	p.rows_aligned = (0 == dims[0] % (uint64_t) vec) ? 1 : 0;
+	p.rows_aligned = (0 == dims[0] % (uint64_t) chunk) ? 1 : 0;
+	p.row_uniform = (0 == dims[0] % (uint64_t) span) ? 1 : 0;
 	int64_t lanes16 = (int64_t) (16 / esize);
 	for (int k = 0; k < ninputs; ++k)
 	{
@@ -406,7 +542,7 @@ int vm_prepare (VmParams& p, int dtype, const uint64_t outshape[LLO_RANK],
 /// Re-shape prepared params for the tile launch if some strided input is
 /// transposed (contiguous along a collapsed dim other than 0).  Returns the
 /// number of staged inputs, 0 when the flat launch should be used.
-static int plan_tiles (VmParams& p, size_t esize, int vec)
+static int plan_tiles (VmParams& p, size_t esize, int chunk, int tile0, int tilep)
 {
 	if (p.ndims < 2 || p.n >= (1ull << 31))
 	{
@@ -463,10 +599,9 @@ static int plan_tiles (VmParams& p, size_t esize, int vec)
 			std::swap(p.in[k].stride[1], p.in[k].stride[pdim]);
 		}
 	}
-	int tile0 = 8 * vec;
 	int nstaged = 0;
 	int64_t lanes16 = (int64_t) (16 / esize);
-	bool rows_aligned = (0 == p.dims[0] % (uint64_t) vec);
+	bool rows_aligned = (0 == p.dims[0] % (uint64_t) chunk);
 	for (int k = 0; k < p.ninputs; ++k)
 	{
 		VmInput& in = p.in[k];
@@ -498,7 +633,7 @@ static int plan_tiles (VmParams& p, size_t esize, int vec)
 	p.out_vec_ok = out_ok ? 1 : 0;
 	p.rows_aligned = 1; // tile chunks never leave their row
 	p.tiles0 = (uint32_t) ((p.dims[0] + tile0 - 1) / tile0);
-	p.tilesp = (uint32_t) ((p.dims[1] + VM_TILEP - 1) / VM_TILEP);
+	p.tilesp = (uint32_t) ((p.dims[1] + tilep - 1) / tilep);
 	return nstaged;
 }
 
@@ -510,13 +645,14 @@ int vm_launch (llo_cuda_ctx* ctx, int dtype, void* out,
 {
 	LLO_DISPATCH_DTYPE(dtype, T,
 	{
-		constexpr int VEC = VmVec<T>::value;
+		using G = VmGeom<T>;
 		VmParams p;
 		LLO_TRY(vm_prepare(p, dtype, outshape, inputs, ninputs,
-			consts, nconsts, program, ninsns, VEC));
+			consts, nconsts, program, ninsns, G::E, VM_THREADS * G::V));
 		p.out = out;
 		p.out_vec_ok = aligned16(out, 0, sizeof(T)) ? 1 : 0;
-		int nstaged = plan_tiles(p, sizeof(T), VEC);
+		size_t spill = (size_t) p.spill_depth * G::V * VM_THREADS * sizeof(T);
+		int nstaged = plan_tiles(p, sizeof(T), G::E, G::TILE0, G::TILEP);
 		if (nstaged > 0)
 		{
 			uint64_t blocks = (uint64_t) p.tiles0 * p.tilesp;
@@ -528,19 +664,30 @@ int vm_launch (llo_cuda_ctx* ctx, int dtype, void* out,
 			{
 				return fail(LLO_ERR_FATAL, "elementwise launch too large");
 			}
-			size_t smem = (size_t) nstaged * VM_TILEP * (8 * VEC + 1) *
-				sizeof(T);
-			vm_tile_kernel<T><<<(unsigned) blocks, 256, smem,
+			size_t smem = (size_t) VM_MAX_TILE_INPUTS * G::TILEP * G::PITCH *
+				sizeof(T) + spill;
+			if (smem > 48 * 1024)
+			{
+				LLO_CUDA_TRY(cudaFuncSetAttribute(vm_tile_kernel<T>,
+					cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+			}
+			vm_tile_kernel<T><<<(unsigned) blocks, VM_THREADS, smem,
 				ctx->stream>>>(p);
 			return launched(ctx, "vm_tile_kernel");
 		}
-		uint64_t nchunks = (p.n + VEC - 1) / VEC;
-		uint64_t blocks = (nchunks + 255) / 256;
+		uint64_t span = (uint64_t) VM_THREADS * G::V;
+		uint64_t blocks = (p.n + span - 1) / span;
 		if (blocks >= 0x7fffffffull)
 		{
 			return fail(LLO_ERR_FATAL, "elementwise launch too large");
 		}
-		vm_flat_kernel<T><<<(unsigned) blocks, 256, 0, ctx->stream>>>(p);
+		if (spill > 48 * 1024)
+		{
+			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_flat_kernel<T>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+		}
+		vm_flat_kernel<T><<<(unsigned) blocks, VM_THREADS, spill,
+			ctx->stream>>>(p);
 		return launched(ctx, "vm_flat_kernel");
 	})
 	return LLO_OK;

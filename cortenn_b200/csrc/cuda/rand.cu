@@ -98,10 +98,8 @@ rand_kernel (int opcode, const __grid_constant__ RandParams p)
 	{
 		T a[1];
 		B b[1];
-		FlatLoader<T,1> load_a = {p.view, i, 1};
-		FlatLoader<B,1> load_b = {p.view, i, 1};
-		load_a.load(a, 0);
-		load_b.load(b, 1);
+		a[0] = load_element<T>(p.view, 0, i);
+		b[0] = load_element<B>(p.view, 1, i);
 		uint32_t r[4];
 		philox4(r, p.seed, p.offset + i, 0);
 		T result;
@@ -226,7 +224,7 @@ extern "C" int llo_cuda_rand (llo_cuda_ctx* ctx, int opcode, int dtype,
 	// the coordinate set-up is shared with the elementwise engine; both
 	// inputs are read one element at a time, so vectors never apply
 	LLO_TRY(vm_prepare(p.view, dtype, outshape, vin, 2, nullptr, 0,
-		prog, 3, 1));
+		prog, 3, 1, 1));
 	p.view.in[0].vec_ok = 0;
 	p.view.in[1].vec_ok = 0;
 	p.out = out;

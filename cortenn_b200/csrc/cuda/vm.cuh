@@ -1,24 +1,28 @@
 ///
 /// vm.cuh — the fused elementwise engine (K1/K2/K3).
 ///
-/// One kernel family evaluates a small stack program per output element:
-/// LOADs read inputs through strided views (the CoordMap of each argument
-/// folded into the load address: contiguous, broadcast, permuted, flipped,
-/// or gathered through an index table), opcodes apply the typed operators
-/// of ops.cuh, the value left on the stack is stored.  A single-operator
-/// call is a 2-4 instruction program; a chain of operators is one pass over
-/// HBM instead of one pass per operator.
+/// One kernel family evaluates a small program per output element: operands
+/// are read through strided views (the CoordMap of each argument folded into
+/// the load address: contiguous, broadcast, permuted, flipped, or gathered
+/// through an index table), opcodes apply the typed operators of ops.cuh, the
+/// result is stored.  A single-operator call is a 2-3 instruction program; a
+/// chain of operators is one pass over HBM instead of one pass per operator.
 ///
-/// Dispatch is warp-uniform (all threads run the same program) and each
-/// thread owns VEC consecutive outputs, so the interpretation cost is
-/// amortised over VEC elements.  The host resolves the stack depth of every
-/// instruction, so the 4 stack slots are plain registers: cheap operators
-/// have one code copy per slot and move nothing, expensive ones (libm-class
-/// math, division) go through one shared copy.  Contiguous inputs / outputs
-/// move as 128-bit vectors.  Two launch shapes:
-///   flat  one chunk of VEC outputs per thread, one CTA per 256 chunks (a
-///         non-persistent grid measured faster than a grid-stride loop on
-///         B200: tools/probes/copy_probe.cu)
+/// The public program (llo_cuda_insn) is a stack program; the host compiles
+/// it to ACCUMULATOR form (vm_encode in elementwise.cu): every instruction
+/// updates one accumulator with an operand that is an input, a constant or a
+/// spilled sub-expression, so the device keeps exactly two value sets in
+/// registers (accumulator + operand), never moves values between slots, and
+/// spills (rare: both operands of an operator are sub-expressions) go to
+/// shared memory.
+///
+/// Dispatch is warp-uniform and amortised over V = 16 elements per thread
+/// (8 for 8-byte types): four 128-bit chunks, each chunk strided by the CTA
+/// width so a warp's request covers 512 contiguous bytes and every thread
+/// keeps 64 bytes per operand in flight.  Two launch shapes:
+///   flat  CTA = 256 threads x V consecutive outputs (a non-persistent grid
+///         measured faster than a grid-stride loop on B200:
+///         tools/probes/copy_probe.cu)
 ///   tile  output tiles for programs with a transposed input: the input
 ///         tile is read along ITS contiguous dimension, staged in padded
 ///         shared memory and consumed transposed, so both the load and the
@@ -79,40 +83,54 @@ __device__ __forceinline__ uint32_t fastdiv (uint32_t n, const FastDiv& f)
 	return (__umulhi(n, f.m) + n) >> f.s;
 }
 
-constexpr int VM_TILEP = 64;   // tile extent along the transposed dim
+constexpr int VM_THREADS = 256;
 constexpr int VM_MAX_TILE_INPUTS = 2;
+constexpr int VM_MAX_CODE = 64;   // accumulator-form instructions
+constexpr int VM_MAX_SPILL = 3;   // spill levels (stack depth 4)
 
-/// Internal instruction: `sel` = operation and stack slot resolved by the
-/// host (see vm_encode in elementwise.cu), `arg` = input / constant number
+/// Per-type geometry: E elements per 128-bit chunk, U chunks per thread
+template <typename T>
+struct VmGeom
+{
+	static constexpr int E = 16 / (int) sizeof(T);
+	static constexpr int U = sizeof(T) >= 4 ? 4 : (sizeof(T) == 2 ? 2 : 1);
+	static constexpr int V = E * U;
+	// tile launch: TILE0 outputs along dim 0 x TILEP along the staged dim
+	static constexpr int TILE0 = 16 * E;
+	static constexpr int TILEP = 16 * U;
+	static constexpr int PITCH = TILE0 + 1;
+};
+
+/// Operand source of an accumulator-form instruction (VmOp::arg >> 4)
+enum VmSrc
+{
+	VM_SRC_NONE = 0,
+	VM_SRC_IN = 1,     // input  (arg & 15)
+	VM_SRC_CONST = 2,  // consts (arg & 15)
+	VM_SRC_POP = 3,    // most recent spill
+};
+
+/// Accumulator-form operations: acc <- f(acc, x), x the operand
+enum VmSel
+{
+	VM_S_SET = 0,   // acc = x
+	VM_S_PUSH,      // spill acc
+	VM_S_ABS, VM_S_NEG, VM_S_ROUND, VM_S_SIN, VM_S_COS, VM_S_TAN, VM_S_EXP,
+	VM_S_LOG, VM_S_SQRT,
+	VM_S_SUM, VM_S_PROD,
+	VM_S_SUB, VM_S_RSUB,     // acc - x, x - acc
+	VM_S_MIN, VM_S_RMIN,     // min(acc, x), min(x, acc)  (std::min argument order)
+	VM_S_MAX, VM_S_RMAX,
+	VM_S_EQ, VM_S_NEQ,
+	VM_S_LT, VM_S_GT,        // acc < x, acc > x
+	VM_S_DIV, VM_S_RDIV,
+	VM_S_POW, VM_S_RPOW,
+};
+
 struct VmOp
 {
 	uint8_t sel;
 	uint8_t arg;
-};
-
-enum VmSel
-{
-	VM_SEL_LOAD = 0,        // +slot written (0..3)
-	VM_SEL_CONST = 4,       // +slot written
-	VM_SEL_ABS = 8,         // unary, +slot (0..3)
-	VM_SEL_NEG = 12,
-	VM_SEL_ROUND = 16,
-	VM_SEL_SUM = 20,        // binary, +destination slot (0..2), rhs = slot + 1
-	VM_SEL_SUB = 23,
-	VM_SEL_PROD = 26,
-	VM_SEL_MIN = 29,
-	VM_SEL_MAX = 32,
-	VM_SEL_EQ = 35,
-	VM_SEL_NEQ = 38,
-	VM_SEL_LT = 41,
-	VM_SEL_GT = 44,
-	VM_SEL_HEAVY = 64,      // + 4 * VmHeavy + slot
-};
-
-enum VmHeavy
-{
-	VM_H_SIN = 0, VM_H_COS, VM_H_TAN, VM_H_EXP, VM_H_LOG, VM_H_SQRT,
-	VM_H_POW, VM_H_DIV, VM_H_COUNT,
 };
 
 struct VmParams
@@ -120,11 +138,13 @@ struct VmParams
 	void* out;
 	uint64_t n;             // output elements
 	int32_t ndims;          // collapsed output dims
-	int32_t rows_aligned;   // dims[0] % VEC == 0: a chunk never straddles a row
+	int32_t rows_aligned;   // dims[0] % E == 0: a chunk never straddles a row
+	int32_t row_uniform;    // dims[0] % (256 * V) == 0: a CTA never does
 	int32_t idx32;          // n < 2^31 and every input offset fits in 32 bits
 	int32_t out_vec_ok;
 	int32_t ninsns;
 	int32_t ninputs;
+	int32_t spill_depth;    // shared-memory spill levels the program needs
 	// tile launch only
 	uint32_t tiles0;
 	uint32_t tilesp;
@@ -133,39 +153,26 @@ struct VmParams
 	FastDiv div[LLO_RANK];
 	VmInput in[LLO_VM_MAX_INPUTS];
 	uint64_t consts[LLO_VM_MAX_CONSTS]; // raw bits of T
-	VmOp code[LLO_VM_MAX_INSNS];
+	VmOp code[VM_MAX_CODE];
 };
 
-template <typename T>
-struct VmVec
-{
-	// outputs per thread
-	static constexpr int value = (sizeof(T) >= 8) ? 4 : 8;
-};
-
-/// 128-bit load of VEC elements when aligned, scalar otherwise.  STREAM
-/// marks data read exactly once (evict-first); views that revisit elements
-/// (broadcasts) keep the default policy so they stay in L1 / L2.
-template <typename T, int VEC, bool STREAM = true>
-__device__ __forceinline__ void load_run (T (&dst)[VEC], const T* src,
+/// E elements from `src`: one 128-bit load when aligned and complete, scalar
+/// loads otherwise.  STREAM marks data read exactly once (evict-first);
+/// views that revisit elements (broadcasts) keep the default policy so they
+/// stay in L1 / L2.
+template <typename T, int E, bool STREAM>
+__device__ __forceinline__ void load_chunk (T* dst, const T* src,
 	bool vec_ok, int valid)
 {
-	constexpr int bytes = VEC * sizeof(T);
-	if constexpr (bytes >= 16)
+	if constexpr (E * sizeof(T) == 16)
 	{
-		if (vec_ok && VEC == valid)
+		if (vec_ok && E == valid)
 		{
-			constexpr int nvec = bytes / 16;
-			const uint4* v = reinterpret_cast<const uint4*>(src);
-			uint4 tmp[nvec];
+			uint4 tmp = STREAM ? __ldcs(reinterpret_cast<const uint4*>(src)) :
+				__ldg(reinterpret_cast<const uint4*>(src));
+			const T* t = reinterpret_cast<const T*>(&tmp);
 #pragma unroll
-			for (int k = 0; k < nvec; ++k)
-			{
-				tmp[k] = STREAM ? __ldcs(v + k) : __ldg(v + k);
-			}
-			const T* t = reinterpret_cast<const T*>(tmp);
-#pragma unroll
-			for (int k = 0; k < VEC; ++k)
+			for (int k = 0; k < E; ++k)
 			{
 				dst[k] = t[k];
 			}
@@ -173,47 +180,33 @@ __device__ __forceinline__ void load_run (T (&dst)[VEC], const T* src,
 		}
 	}
 #pragma unroll
-	for (int k = 0; k < VEC; ++k)
+	for (int k = 0; k < E; ++k)
 	{
-		if (k < valid)
-		{
-			dst[k] = __ldg(src + k);
-		}
-		else
-		{
-			dst[k] = T();
-		}
+		dst[k] = (k < valid) ? __ldg(src + k) : T();
 	}
 }
 
-template <typename T, int VEC>
-__device__ __forceinline__ void store_run (T* dst, const T (&src)[VEC],
+template <typename T, int E>
+__device__ __forceinline__ void store_chunk (T* dst, const T* src,
 	bool vec_ok, int valid)
 {
-	constexpr int bytes = VEC * sizeof(T);
-	if constexpr (bytes >= 16)
+	if constexpr (E * sizeof(T) == 16)
 	{
-		if (vec_ok && VEC == valid)
+		if (vec_ok && E == valid)
 		{
-			constexpr int nvec = bytes / 16;
-			uint4 tmp[nvec];
-			T* t = reinterpret_cast<T*>(tmp);
+			uint4 tmp;
+			T* t = reinterpret_cast<T*>(&tmp);
 #pragma unroll
-			for (int k = 0; k < VEC; ++k)
+			for (int k = 0; k < E; ++k)
 			{
 				t[k] = src[k];
 			}
-			uint4* v = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-			for (int k = 0; k < nvec; ++k)
-			{
-				__stcs(v + k, tmp[k]);
-			}
+			__stcs(reinterpret_cast<uint4*>(dst), tmp);
 			return;
 		}
 	}
 #pragma unroll
-	for (int k = 0; k < VEC; ++k)
+	for (int k = 0; k < E; ++k)
 	{
 		if (k < valid)
 		{
@@ -254,23 +247,23 @@ __device__ __forceinline__ int64_t strided_offset (const VmParams& p,
 	return off;
 }
 
-/// VEC values of a strided input starting at element offset `off` and
-/// running along output dim 0
-template <typename T, int VEC>
-__device__ __forceinline__ void load_strided_run (T (&dst)[VEC],
+/// E values of a strided input starting at element offset `off` and running
+/// along output dim 0
+template <typename T, int E>
+__device__ __forceinline__ void load_strided_chunk (T* dst,
 	const VmInput& in, int64_t off, int valid)
 {
 	const T* data = static_cast<const T*>(in.data);
 	int64_t s0 = in.stride[0];
 	if (1 == s0)
 	{
-		load_run<T,VEC,false>(dst, data + off, in.vec_ok, valid);
+		load_chunk<T,E,false>(dst, data + off, in.vec_ok, valid);
 	}
 	else if (0 == s0)
 	{
 		T v = __ldg(data + off);
 #pragma unroll
-		for (int k = 0; k < VEC; ++k)
+		for (int k = 0; k < E; ++k)
 		{
 			dst[k] = v;
 		}
@@ -278,158 +271,202 @@ __device__ __forceinline__ void load_strided_run (T (&dst)[VEC],
 	else
 	{
 #pragma unroll
-		for (int k = 0; k < VEC; ++k)
+		for (int k = 0; k < E; ++k)
 		{
 			dst[k] = (k < valid) ? __ldg(data + off + k * s0) : T();
 		}
 	}
 }
 
-/// Input access of the flat launch: chunk [base, base + valid) of the
-/// output's linear index space
-template <typename T, int VEC>
+/// Single-element access through the view machinery (random fills)
+template <typename T>
+__device__ __forceinline__ T load_element (const VmParams& p, int k, uint64_t i)
+{
+	const VmInput& in = p.in[k];
+	const T* data = static_cast<const T*>(in.data);
+	if (VM_IN_LINEAR == in.mode)
+	{
+		return __ldg(data + in.offset + i);
+	}
+	if (VM_IN_INDEXED == in.mode)
+	{
+		return __ldg(data + __ldg(in.index + i));
+	}
+	return __ldg(data + strided_offset(p, in, i));
+}
+
+/// Input access of the flat launch.  Chunk u of thread t covers the outputs
+/// [base + (u * 256 + t) * E, +E)
+template <typename T>
 struct FlatLoader
 {
-	const VmParams& p;
-	uint64_t base;
-	int valid;
+	using G = VmGeom<T>;
 
-	__device__ __forceinline__ void load (T (&dst)[VEC], int k) const
+	const VmParams& p;
+	uint64_t base;   // first output of this CTA
+	bool full;       // the CTA's 256 * V outputs all exist
+
+	__device__ __forceinline__ uint64_t first (int u) const
+	{
+		return base + (uint64_t) ((u * VM_THREADS + (int) threadIdx.x) * G::E);
+	}
+
+	__device__ __forceinline__ int valid (int u) const
+	{
+		if (full)
+		{
+			return G::E;
+		}
+		uint64_t e0 = first(u);
+		if (e0 >= p.n)
+		{
+			return 0;
+		}
+		uint64_t left = p.n - e0;
+		return left < (uint64_t) G::E ? (int) left : G::E;
+	}
+
+	__device__ __forceinline__ void load (T (&x)[G::V], int k) const
 	{
 		const VmInput& in = p.in[k];
 		const T* data = static_cast<const T*>(in.data);
 		if (VM_IN_LINEAR == in.mode)
 		{
-			load_run<T,VEC>(dst, data + in.offset + base, in.vec_ok, valid);
+			const T* src = data + in.offset + first(0);
+#pragma unroll
+			for (int u = 0; u < G::U; ++u)
+			{
+				load_chunk<T,G::E,true>(x + u * G::E,
+					src + u * VM_THREADS * G::E, in.vec_ok, valid(u));
+			}
 		}
 		else if (VM_IN_INDEXED == in.mode)
 		{
 #pragma unroll
-			for (int e = 0; e < VEC; ++e)
+			for (int u = 0; u < G::U; ++u)
 			{
-				dst[e] = (e < valid) ?
-					__ldg(data + __ldg(in.index + base + e)) : T();
+				uint64_t e0 = first(u);
+				int ok = valid(u);
+#pragma unroll
+				for (int e = 0; e < G::E; ++e)
+				{
+					x[u * G::E + e] = (e < ok) ?
+						__ldg(data + __ldg(in.index + e0 + e)) : T();
+				}
+			}
+		}
+		else if (p.row_uniform)
+		{
+			// the CTA sits inside one row: only the dim-0 coordinate moves
+			int64_t off = strided_offset(p, in, first(0));
+			int64_t step = (int64_t) (VM_THREADS * G::E) * in.stride[0];
+#pragma unroll
+			for (int u = 0; u < G::U; ++u)
+			{
+				load_strided_chunk<T,G::E>(x + u * G::E, in, off + u * step,
+					G::E);
 			}
 		}
 		else if (p.rows_aligned)
 		{
-			// the chunk shares every coordinate but the fastest
-			load_strided_run<T,VEC>(dst, in, strided_offset(p, in, base),
-				valid);
+			// a chunk shares every coordinate but the fastest
+#pragma unroll
+			for (int u = 0; u < G::U; ++u)
+			{
+				int ok = valid(u);
+				int64_t off = ok > 0 ? strided_offset(p, in, first(u)) : in.offset;
+				load_strided_chunk<T,G::E>(x + u * G::E, in, off, ok);
+			}
 		}
 		else
 		{
 			// chunks may straddle rows: address every element on its own
 #pragma unroll
-			for (int e = 0; e < VEC; ++e)
+			for (int u = 0; u < G::U; ++u)
 			{
-				dst[e] = (e < valid) ?
-					__ldg(data + strided_offset(p, in, base + e)) : T();
+				uint64_t e0 = first(u);
+				int ok = valid(u);
+#pragma unroll
+				for (int e = 0; e < G::E; ++e)
+				{
+					x[u * G::E + e] = (e < ok) ?
+						__ldg(data + strided_offset(p, in, e0 + e)) : T();
+				}
 			}
 		}
 	}
 };
 
 #define LLO_VM_EACH(BODY) _Pragma("unroll")\
-	for (int k = 0; k < VEC; ++k) { BODY; }
+	for (int e = 0; e < V; ++e) { BODY; }
 
-/// Run the program for one chunk; the result is left in s0
-template <typename T, int VEC, typename Loader>
-__device__ __forceinline__ void vm_run (T (&s0)[VEC], const VmParams& p,
-	const Loader& loader)
+/// Run the accumulator program for this thread's V outputs.  `spill` is the
+/// CTA's shared-memory spill area ([level][element][thread]).
+template <typename T, typename Loader>
+__device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
+	const VmParams& p, const Loader& loader, T* spill)
 {
-	T s1[VEC];
-	T s2[VEC];
-	T s3[VEC];
+	constexpr int V = VmGeom<T>::V;
+	int depth = 0;
+#pragma unroll 1
 	for (int pc = 0; pc < p.ninsns; ++pc)
 	{
 		int sel = p.code[pc].sel;
 		int arg = p.code[pc].arg;
-		if (sel < VM_SEL_ABS)
+		int src = arg >> 4;
+		T x[V];
+		if (VM_SRC_IN == src)
 		{
-			// LOAD / CONST: fetch once, then move into the slot
-			T t[VEC];
-			if (sel < VM_SEL_CONST)
-			{
-				loader.load(t, arg);
-			}
-			else
-			{
-				T c;
-				memcpy(&c, &p.consts[arg], sizeof(T));
-				LLO_VM_EACH(t[k] = c)
-			}
-			switch (sel & 3)
-			{
-				case 0: LLO_VM_EACH(s0[k] = t[k]) break;
-				case 1: LLO_VM_EACH(s1[k] = t[k]) break;
-				case 2: LLO_VM_EACH(s2[k] = t[k]) break;
-				default: LLO_VM_EACH(s3[k] = t[k]) break;
-			}
+			loader.load(x, arg & 15);
 		}
-		else if (sel < VM_SEL_HEAVY)
+		else if (VM_SRC_CONST == src)
 		{
-			switch (sel)
-			{
-#define LLO_VM_UNARY(SEL, FN)\
-				case SEL + 0: LLO_VM_EACH(s0[k] = FN(s0[k])) break;\
-				case SEL + 1: LLO_VM_EACH(s1[k] = FN(s1[k])) break;\
-				case SEL + 2: LLO_VM_EACH(s2[k] = FN(s2[k])) break;\
-				case SEL + 3: LLO_VM_EACH(s3[k] = FN(s3[k])) break;
-				LLO_VM_UNARY(VM_SEL_ABS, m_abs)
-				LLO_VM_UNARY(VM_SEL_NEG, m_neg)
-				LLO_VM_UNARY(VM_SEL_ROUND, m_round)
-#undef LLO_VM_UNARY
-#define LLO_VM_BINARY(SEL, EXPR)\
-				case SEL + 0: LLO_VM_EACH(T a = s0[k]; T b = s1[k]; s0[k] = EXPR) break;\
-				case SEL + 1: LLO_VM_EACH(T a = s1[k]; T b = s2[k]; s1[k] = EXPR) break;\
-				case SEL + 2: LLO_VM_EACH(T a = s2[k]; T b = s3[k]; s2[k] = EXPR) break;
-				LLO_VM_BINARY(VM_SEL_SUM, m_add(a, b))
-				LLO_VM_BINARY(VM_SEL_SUB, m_sub(a, b))
-				LLO_VM_BINARY(VM_SEL_PROD, m_mul(a, b))
-				LLO_VM_BINARY(VM_SEL_MIN, m_min(a, b))
-				LLO_VM_BINARY(VM_SEL_MAX, m_max(a, b))
-				LLO_VM_BINARY(VM_SEL_EQ, (T) (a == b))
-				LLO_VM_BINARY(VM_SEL_NEQ, (T) (a != b))
-				LLO_VM_BINARY(VM_SEL_LT, (T) (a < b))
-				LLO_VM_BINARY(VM_SEL_GT, (T) (a > b))
-#undef LLO_VM_BINARY
-				default: break;
-			}
+			T c;
+			memcpy(&c, &p.consts[arg & 15], sizeof(T));
+			LLO_VM_EACH(x[e] = c)
 		}
-		else
+		else if (VM_SRC_POP == src)
 		{
-			// one shared copy of the expensive math: operands are moved out
-			// of, and the result back into, the slot
-			int slot = sel & 3;
-			int hop = (sel - VM_SEL_HEAVY) >> 2;
-			T a[VEC];
-			T b[VEC];
-			switch (slot)
+			--depth;
+			const T* sp = spill + (size_t) depth * V * VM_THREADS + threadIdx.x;
+			LLO_VM_EACH(x[e] = sp[e * VM_THREADS])
+		}
+		switch (sel)
+		{
+			case VM_S_SET: LLO_VM_EACH(acc[e] = x[e]) break;
+			case VM_S_PUSH:
 			{
-				case 0: LLO_VM_EACH(a[k] = s0[k]; b[k] = s1[k]) break;
-				case 1: LLO_VM_EACH(a[k] = s1[k]; b[k] = s2[k]) break;
-				case 2: LLO_VM_EACH(a[k] = s2[k]; b[k] = s3[k]) break;
-				default: LLO_VM_EACH(a[k] = s3[k]; b[k] = s3[k]) break;
+				T* sp = spill + (size_t) depth * V * VM_THREADS + threadIdx.x;
+				LLO_VM_EACH(sp[e * VM_THREADS] = acc[e])
+				++depth;
 			}
-			switch (hop)
-			{
-				case VM_H_SIN: LLO_VM_EACH(a[k] = m_sin(a[k])) break;
-				case VM_H_COS: LLO_VM_EACH(a[k] = m_cos(a[k])) break;
-				case VM_H_TAN: LLO_VM_EACH(a[k] = m_tan(a[k])) break;
-				case VM_H_EXP: LLO_VM_EACH(a[k] = m_exp(a[k])) break;
-				case VM_H_LOG: LLO_VM_EACH(a[k] = m_log(a[k])) break;
-				case VM_H_SQRT: LLO_VM_EACH(a[k] = m_sqrt(a[k])) break;
-				case VM_H_POW: LLO_VM_EACH(a[k] = m_pow(a[k], b[k])) break;
-				default: LLO_VM_EACH(a[k] = m_div(a[k], b[k])) break;
-			}
-			switch (slot)
-			{
-				case 0: LLO_VM_EACH(s0[k] = a[k]) break;
-				case 1: LLO_VM_EACH(s1[k] = a[k]) break;
-				case 2: LLO_VM_EACH(s2[k] = a[k]) break;
-				default: LLO_VM_EACH(s3[k] = a[k]) break;
-			}
+				break;
+			case VM_S_ABS: LLO_VM_EACH(acc[e] = m_abs(acc[e])) break;
+			case VM_S_NEG: LLO_VM_EACH(acc[e] = m_neg(acc[e])) break;
+			case VM_S_ROUND: LLO_VM_EACH(acc[e] = m_round(acc[e])) break;
+			case VM_S_SIN: LLO_VM_EACH(acc[e] = m_sin(acc[e])) break;
+			case VM_S_COS: LLO_VM_EACH(acc[e] = m_cos(acc[e])) break;
+			case VM_S_TAN: LLO_VM_EACH(acc[e] = m_tan(acc[e])) break;
+			case VM_S_EXP: LLO_VM_EACH(acc[e] = m_exp(acc[e])) break;
+			case VM_S_LOG: LLO_VM_EACH(acc[e] = m_log(acc[e])) break;
+			case VM_S_SQRT: LLO_VM_EACH(acc[e] = m_sqrt(acc[e])) break;
+			case VM_S_SUM: LLO_VM_EACH(acc[e] = m_add(acc[e], x[e])) break;
+			case VM_S_PROD: LLO_VM_EACH(acc[e] = m_mul(acc[e], x[e])) break;
+			case VM_S_SUB: LLO_VM_EACH(acc[e] = m_sub(acc[e], x[e])) break;
+			case VM_S_RSUB: LLO_VM_EACH(acc[e] = m_sub(x[e], acc[e])) break;
+			case VM_S_MIN: LLO_VM_EACH(acc[e] = m_min(acc[e], x[e])) break;
+			case VM_S_RMIN: LLO_VM_EACH(acc[e] = m_min(x[e], acc[e])) break;
+			case VM_S_MAX: LLO_VM_EACH(acc[e] = m_max(acc[e], x[e])) break;
+			case VM_S_RMAX: LLO_VM_EACH(acc[e] = m_max(x[e], acc[e])) break;
+			case VM_S_EQ: LLO_VM_EACH(acc[e] = (T) (acc[e] == x[e])) break;
+			case VM_S_NEQ: LLO_VM_EACH(acc[e] = (T) (acc[e] != x[e])) break;
+			case VM_S_LT: LLO_VM_EACH(acc[e] = (T) (acc[e] < x[e])) break;
+			case VM_S_GT: LLO_VM_EACH(acc[e] = (T) (acc[e] > x[e])) break;
+			case VM_S_DIV: LLO_VM_EACH(acc[e] = m_div(acc[e], x[e])) break;
+			case VM_S_RDIV: LLO_VM_EACH(acc[e] = m_div(x[e], acc[e])) break;
+			case VM_S_POW: LLO_VM_EACH(acc[e] = m_pow(acc[e], x[e])) break;
+			case VM_S_RPOW: LLO_VM_EACH(acc[e] = m_pow(x[e], acc[e])) break;
+			default: break;
 		}
 	}
 }
@@ -442,10 +479,11 @@ int vm_launch (llo_cuda_ctx* ctx, int dtype, void* out,
 	const llo_cuda_insn* program, int ninsns);
 
 /// Fill the shape-dependent part of VmParams (collapsing compatible dims);
-/// shared with the random fills
+/// shared with the random fills.  `chunk` = elements per 128-bit chunk,
+/// `span` = outputs per CTA (rows_aligned / row_uniform are relative to them)
 int vm_prepare (VmParams& p, int dtype, const uint64_t outshape[LLO_RANK],
 	const VmInput* inputs, int ninputs, const void* consts, int nconsts,
-	const llo_cuda_insn* program, int ninsns, int vec);
+	const llo_cuda_insn* program, int ninsns, int chunk, int span);
 
 }
 
