@@ -93,6 +93,12 @@ EXPORTS = {
     "llo_cuda_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
                                 C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                 C.c_void_p, C.c_int64, C.c_int64, C.c_int]),
+    "llo_cuda_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "llo_cuda_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "llo_cuda_comm_destroy": (C.c_int, [C.c_void_p]),
+    "llo_cuda_comm_rank": (C.c_int, [C.c_void_p]),
+    "llo_cuda_comm_size": (C.c_int, [C.c_void_p]),
+    "llo_cuda_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int]),
 }
 
 _lib = None
@@ -104,7 +110,7 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise OSError("%s not built; run `python -m cortenn_b200.build`" % LIB_PATH)
+            raise OSError("%s not built; run `python cortenn_b200/build.py`" % LIB_PATH)
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(handle, name)  # AttributeError if not exported

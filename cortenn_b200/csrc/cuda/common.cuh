@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -29,6 +30,10 @@ struct llo_cuda_ctx
 	int reduce_mode = LLO_REDUCE_TREE;
 	// device-side error flag raised by kernels that validate coordinates
 	int* dev_error = nullptr;
+	// K8: NCCL communicator of the batch-sharded executor (comm.cu)
+	void* comm = nullptr;
+	int comm_rank = 0;
+	int comm_size = 1;
 };
 
 namespace llo_cuda

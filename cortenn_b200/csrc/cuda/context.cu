@@ -121,6 +121,7 @@ int llo_cuda_destroy (llo_cuda_ctx* ctx)
 		return LLO_OK;
 	}
 	cudaSetDevice(ctx->device);
+	llo_cuda_comm_destroy(ctx);
 	cudaStreamSynchronize(ctx->stream);
 	cudaFree(ctx->dev_error);
 	if (ctx->own_stream)

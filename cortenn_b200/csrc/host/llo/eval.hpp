@@ -73,6 +73,12 @@ GenericData eval (ade::TensptrT tens, age::_GENERATED_DTYPE dtype);
 /// Same, but the result stays on the device (`device_` set, `data_` null)
 GenericData eval_device (ade::TensptrT tens, age::_GENERATED_DTYPE dtype);
 
+/// Evaluate several roots of one graph together: sub-graphs they share (the
+/// forward pass under the gradients of llo::derive) are computed once.
+/// Results stay on the device.
+std::vector<GenericData> eval_device_many (ade::TensT roots,
+	age::_GENERATED_DTYPE dtype);
+
 }
 
 #endif // LLO_EVAL_HPP

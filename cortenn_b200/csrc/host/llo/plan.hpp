@@ -51,6 +51,10 @@ struct PlanStats
 /// Evaluate `root` as `dtype` on the device; the result stays in HBM
 GenericData planned_eval (ade::TensptrT root, age::_GENERATED_DTYPE dtype);
 
+/// Evaluate several roots in one plan (shared sub-graphs computed once)
+std::vector<GenericData> planned_eval_many (const ade::TensT& roots,
+	age::_GENERATED_DTYPE dtype);
+
 /// Statistics of the most recent planned_eval on this thread
 const PlanStats& last_plan_stats (void);
 

@@ -89,6 +89,24 @@ GenericData eval_device (ade::TensptrT tens, age::_GENERATED_DTYPE dtype)
 	return eval.out_;
 }
 
+std::vector<GenericData> eval_device_many (ade::TensT roots,
+	age::_GENERATED_DTYPE dtype)
+{
+	if (0 != get_option("plan"))
+	{
+		return planned_eval_many(roots, dtype);
+	}
+	std::shared_ptr<EvalMemo> memo = std::make_shared<EvalMemo>();
+	std::vector<GenericData> outs;
+	for (ade::TensptrT& root : roots)
+	{
+		Evaluator eval(dtype, memo);
+		root->accept(eval);
+		outs.push_back(eval.out_);
+	}
+	return outs;
+}
+
 GenericData eval (ade::TensptrT tens, age::_GENERATED_DTYPE dtype)
 {
 	GenericData out = eval_device(tens, dtype);

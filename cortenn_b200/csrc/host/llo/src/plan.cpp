@@ -1158,18 +1158,38 @@ static thread_local PlanStats last_stats;
 
 }
 
+std::vector<GenericData> planned_eval_many (const ade::TensT& roots,
+	age::_GENERATED_DTYPE dtype)
+{
+	// one plan for every root: sub-graphs the roots share (the forward pass
+	// under a set of gradients) are computed once
+	Plan plan(dtype);
+	std::vector<PNode*> tops;
+	for (const ade::TensptrT& root : roots)
+	{
+		tops.push_back(plan.build(root.get(), dtype));
+	}
+	for (PNode* top : tops)
+	{
+		plan.count_uses(top);
+	}
+	std::vector<GenericData> outs;
+	for (PNode* top : tops)
+	{
+		plan.evaluate(top);
+		GenericData out;
+		out.shape_ = top->shape_;
+		out.dtype_ = dtype;
+		out.device_ = top->data_;
+		outs.push_back(out);
+	}
+	last_stats = plan.stats_;
+	return outs;
+}
+
 GenericData planned_eval (ade::TensptrT root, age::_GENERATED_DTYPE dtype)
 {
-	Plan plan(dtype);
-	PNode* top = plan.build(root.get(), dtype);
-	plan.count_uses(top);
-	plan.evaluate(top);
-	last_stats = plan.stats_;
-	GenericData out;
-	out.shape_ = top->shape_;
-	out.dtype_ = dtype;
-	out.device_ = top->data_;
-	return out;
+	return planned_eval_many(ade::TensT{root}, dtype)[0];
 }
 
 const PlanStats& last_plan_stats (void)

@@ -152,6 +152,18 @@ struct DeviceResult
 	llo::GenericData data_;
 };
 
+/// Flat device buffer: the packed gradient vector of the batch-sharded
+/// executor (one allreduce per gradient evaluation instead of one per tensor)
+struct DeviceBuffer
+{
+	DeviceBuffer (size_t nbytes) :
+		nbytes_(nbytes), data_(llo::device::alloc(nbytes)) {}
+
+	size_t nbytes_;
+
+	std::shared_ptr<char> data_;
+};
+
 }
 
 PYBIND11_MODULE(_C, m)
@@ -346,6 +358,110 @@ PYBIND11_MODULE(_C, m)
 			}
 			return out;
 		}, py::arg("tens"), py::arg("dtype") = py::dtype::of<double>());
+	llo_m.def("evaluate_device_many", [](std::vector<T> roots, py::dtype dtype)
+		{
+			age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);
+			std::vector<llo::GenericData> datas;
+			{
+				py::gil_scoped_release release;
+				datas = llo::eval_device_many(roots, ctype);
+			}
+			std::vector<pyllo::DeviceResult> outs;
+			for (llo::GenericData& d : datas)
+			{
+				outs.push_back(pyllo::DeviceResult{d});
+			}
+			return outs;
+		}, "evaluate several roots of one graph together; shared sub-graphs "
+		"are computed once and the results stay on the device",
+		py::arg("roots"), py::arg("dtype") = py::dtype::of<double>());
+
+	py::class_<pyllo::DeviceBuffer>(llo_m, "DeviceBuffer")
+		.def(py::init<size_t>(), py::arg("nbytes"))
+		.def("ptr", [](pyllo::DeviceBuffer& self)
+			{ return (uintptr_t) self.data_.get(); })
+		.def("nbytes", [](pyllo::DeviceBuffer& self) { return self.nbytes_; })
+		.def("store", [](pyllo::DeviceBuffer& self, size_t offset,
+			pyllo::DeviceResult& src)
+			{
+				size_t n = src.data_.nbytes();
+				if (offset + n > self.nbytes_)
+				{
+					logs::fatalf("cannot store %d bytes at offset %d of a "
+						"%d-byte buffer", (int) n, (int) offset, (int) self.nbytes_);
+				}
+				llo::device::check(llo_cuda_d2d(llo::device::ctx(),
+					self.data_.get() + offset, src.data_.device_.get(), n));
+			}, "device-to-device copy of a result into the buffer",
+			py::arg("offset"), py::arg("src"))
+		.def("upload", [](pyllo::DeviceBuffer& self, size_t offset, py::array data)
+			{
+				py::array dense = py::array::ensure(data, py::array::c_style);
+				size_t n = (size_t) dense.nbytes();
+				if (offset + n > self.nbytes_)
+				{
+					logs::fatal("upload past the end of the buffer");
+				}
+				llo::device::check(llo_cuda_h2d(llo::device::ctx(),
+					self.data_.get() + offset, dense.data(), n));
+			}, py::arg("offset"), py::arg("data"))
+		.def("numpy", [](pyllo::DeviceBuffer& self, py::dtype dtype,
+			size_t offset, size_t count)
+			{
+				py::array out(dtype, std::vector<py::ssize_t>{(py::ssize_t) count});
+				size_t n = count * (size_t) dtype.itemsize();
+				if (offset + n > self.nbytes_)
+				{
+					logs::fatal("read past the end of the buffer");
+				}
+				llo::device::check(llo_cuda_d2h(llo::device::ctx(),
+					out.mutable_data(), self.data_.get() + offset, n));
+				return out;
+			}, py::arg("dtype"), py::arg("offset"), py::arg("count"))
+		.def("allreduce", [](pyllo::DeviceBuffer& self, py::dtype dtype,
+			std::string opname, bool ordered)
+			{
+				age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);
+				age::_GENERATED_OPCODE code = age::get_op(opname);
+				size_t count = self.nbytes_ / (size_t) dtype.itemsize();
+				py::gil_scoped_release release;
+				llo::device::check(llo_cuda_allreduce(llo::device::ctx(),
+					self.data_.get(), count, (int) ctype, (int) code,
+					ordered ? LLO_ALLREDUCE_ORDERED : LLO_ALLREDUCE_FAST));
+			}, "fold the buffer in place over every rank of the context's "
+			"communicator (K8)",
+			py::arg("dtype"), py::arg("op") = "SUM", py::arg("ordered") = false);
+
+	llo_m.def("comm_unique_id", []()
+		{
+			char id[128];
+			llo::device::check(llo_cuda_comm_unique_id(id));
+			return py::bytes(id, 128);
+		}, "NCCL unique id (rank 0 creates it, every rank receives it)");
+	llo_m.def("comm_init", [](int rank, int nranks, py::bytes id)
+		{
+			std::string raw = id;
+			if (nranks > 1 && raw.size() != 128)
+			{
+				logs::fatal("a communicator id is 128 bytes");
+			}
+			raw.resize(128);
+			py::gil_scoped_release release;
+			llo::device::check(llo_cuda_comm_init(llo::device::ctx(),
+				rank, nranks, raw.data()));
+		}, py::arg("rank"), py::arg("nranks"), py::arg("id") = py::bytes(""));
+	llo_m.def("comm_destroy", []()
+		{ llo::device::check(llo_cuda_comm_destroy(llo::device::ctx())); });
+	llo_m.def("comm_size", []()
+		{ return llo_cuda_comm_size(llo::device::ctx()); });
+	llo_m.def("comm_rank", []()
+		{ return llo_cuda_comm_rank(llo::device::ctx()); });
+	llo_m.def("set_stream", [](uintptr_t stream)
+		{
+			llo::device::check(llo_cuda_set_stream(llo::device::ctx(),
+				(void*) stream));
+		}, "run the evaluator on an external cudaStream_t (0 = its own)");
+
 	llo_m.def("available", []() { return llo::device::available(); });
 	llo_m.def("sync", []()
 		{ llo::device::check(llo_cuda_sync(llo::device::ctx())); });

@@ -206,6 +206,26 @@ int llo_cuda_gemm (llo_cuda_ctx* ctx, int dtype,
 	void* C, int64_t c_rs, int64_t c_cs,
 	int precision);
 
+/* ---- K8: the exchange step of batch-sharded evaluation (no counterpart in
+ *      the reference, which has no communication layer: SURVEY.md 2.2).  One
+ *      context per GPU / process; rank 0 creates a 128-byte NCCL unique id,
+ *      the host passes it to every rank (any out-of-band channel), every rank
+ *      calls llo_cuda_comm_init.  llo_cuda_allreduce folds `n` elements of
+ *      `buf` in place over all ranks with SUM / PROD / MIN / MAX on the
+ *      context's stream.  mode LLO_ALLREDUCE_FAST = ncclAllReduce (ring / tree
+ *      / NVLS as NCCL chooses; run-to-run deterministic for a fixed topology),
+ *      LLO_ALLREDUCE_ORDERED = all-gather + fold in rank order (bit-identical
+ *      on every rank and independent of NCCL's algorithm).  nranks == 1 is a
+ *      no-op and needs no NCCL. ---- */
+enum { LLO_ALLREDUCE_FAST = 0, LLO_ALLREDUCE_ORDERED = 1 };
+int llo_cuda_comm_unique_id (void* id128);
+int llo_cuda_comm_init (llo_cuda_ctx* ctx, int rank, int nranks, const void* id128);
+int llo_cuda_comm_destroy (llo_cuda_ctx* ctx);
+int llo_cuda_comm_rank (llo_cuda_ctx* ctx);
+int llo_cuda_comm_size (llo_cuda_ctx* ctx);
+int llo_cuda_allreduce (llo_cuda_ctx* ctx, void* buf, uint64_t n, int dtype,
+	int opcode, int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,11 @@ def pytest_configure(config):
 
 
 def _ensure_built():
-    from cortenn_b200 import build as product_build
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "_cortenn_b200_build", os.path.join(ROOT, "cortenn_b200", "build.py"))
+    product_build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(product_build)
     if not (os.path.exists(product_build.cuda_lib_path()) and
             os.path.exists(product_build.host_lib_path())):
         product_build.build_all()
