@@ -8,13 +8,16 @@ Headline workload (BASELINE.json configs[1]): the elementwise chain
     out = add(mul(exp(x), extend(b, 1, {D})), permute(x, {1,0}))
 over N = 2^28 fp32 elements, x as [D, D] with D = 16384, built with the
 reference's `age` graph API and evaluated through llo.evaluate_device (value,
-inputs resident in HBM) and llo.evaluate with host buffers (e2e).  A "step" is
-one evaluation of that graph.  Metric: algorithmic HBM GB/s =
+inputs resident in HBM) and llo.evaluate with pinned host buffers (e2e).  A
+"step" is one evaluation of that graph.  Metric: algorithmic HBM GB/s =
 4 * (N + D + N) bytes / step time, whole job over all
 ranks.  With --gpus N > 1 every rank evaluates its own replica of the chain
-(the single-operator configs do not shard: "replicas only", weak scaling);
-the batch-sharded MLP gradient evaluation with its NCCL allreduce is reported
-under "workloads" for every N.
+(the single-operator configs do not shard: "replicas only", weak scaling).
+
+The other BASELINE.json configurations are reported under "workloads":
+reductions of [D, D] (config 3), matmul 8192^3 fp32 (config 4) and the
+batch-sharded MLP gradient evaluation with its NCCL allreduce (config 5, batch
+65536 split over the N ranks: strong scaling of that workload).
 
 One JSON line on stdout (rank 0).
 """
@@ -24,7 +27,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -32,8 +34,11 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+import workloads  # noqa: E402
+
 METRIC = "elementwise_chain_hbm_gbps"
 UNIT = "GB/s"
+F32 = np.dtype(np.float32)
 
 
 def env_int(name, default):
@@ -48,8 +53,17 @@ def measured_peaks():
     if os.path.exists(path):
         with open(path) as fh:
             data = json.load(fh)
-        return float(data["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(data["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ffma_peak():
+    """fp32 FFMA issue peak measured by tools/probes/fma_peak.cu on this pool"""
+    path = os.path.join(ROOT, "profiles", "fma_peak.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["ffma_tflops"]), "measured (profiles/fma_peak.json)"
+    return 148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1965 MHz"
 
 
 class ClockSampler:
@@ -72,6 +86,7 @@ class ClockSampler:
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
                  "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.3)    # let the first samples land before the timed region
         except OSError:
             self.proc = None
 
@@ -85,7 +100,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        clocks, reasons, maxes = [], set(), []
+        clocks, reasons, maxes, power = [], set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             with open(self.path) as fh:
@@ -96,6 +111,7 @@ class ClockSampler:
                     try:
                         clocks.append(float(cols[0]))
                         maxes.append(float(cols[1]))
+                        power.append(float(cols[2]))
                     except ValueError:
                         continue
                     for name, val in zip(names, cols[3:7]):
@@ -107,77 +123,62 @@ class ClockSampler:
         if clocks:
             out["sm_mhz"] = float(np.median(clocks))
             out["sm_max_mhz"] = float(max(maxes))
+            out["power_w_max"] = float(max(power)) if power else None
             out["samples"] = len(clocks)
         out["reasons"] = sorted(reasons)
         return out
 
 
-# ---- the chain graph ------------------------------------------------------------
+# ---- CPU baseline / reference arm ------------------------------------------------------
 
-def chain_inputs(side, seed_x=2, seed_b=3):
-    x = np.random.default_rng(seed_x).uniform(0.5, 2.0, (side, side)).astype(np.float32)
-    b = np.random.default_rng(seed_b).uniform(0.5, 2.0, (side,)).astype(np.float32)
-    return x, b
-
-
-def chain_graph(age, llo, x, b):
-    side = x.shape[0]
-    vx = llo.variable(x, "x")
-    vb = llo.variable(b, "b")
-    root = age.add(age.mul(age.exp(vx), age.extend(vb, 1, [side])), age.permute(vx, [1, 0]))
-    return vx, vb, root
-
-
-def chain_bytes(side):
-    n = side * side
-    return 4 * (n + side + n)
+def oracle_module():
+    """the oracle (CPU restatement of the reference evaluator): checker and
+    CPU baseline only, never on the product path"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    return util.oracle
 
 
 def cpu_chain(side, repeats):
-    """The oracle (CPU restatement of the reference evaluator) on a bounded
-    sample of the chain.  Returns (seconds per evaluation, GB/s)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import util  # oracle access
+    """The oracle on a bounded sample of the chain: (seconds per evaluation, GB/s)."""
     from cortenn_b200 import age, llo
-    x, b = chain_inputs(side)
-    _, _, root = chain_graph(age, llo, x, b)
+    oracle = oracle_module()
+    x, b = workloads.chain_inputs(side)
+    _, _, root = workloads.chain_graph(age, llo, x, b)
     times = []
     for _ in range(repeats):
         t0 = time.perf_counter()
-        util.oracle.evaluate(root, np.dtype(np.float32))
+        oracle.evaluate(root, F32)
         times.append(time.perf_counter() - t0)
     sec = float(np.median(times))
-    return sec, chain_bytes(side) / sec / 1e9
+    return sec, workloads.chain_bytes(side) / sec / 1e9
 
-
-# ---- reference arm ----------------------------------------------------------------
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     side = 1 << (args.ref_log2n // 2)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import util
     from cortenn_b200 import age, llo
-    x, b = chain_inputs(side)
-    _, _, root = chain_graph(age, llo, x, b)
+    oracle = oracle_module()
+    x, b = workloads.chain_inputs(side)
+    _, _, root = workloads.chain_graph(age, llo, x, b)
     for _ in range(args.warmup):
-        util.oracle.evaluate(root, np.dtype(np.float32))
+        oracle.evaluate(root, F32)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        util.oracle.evaluate(root, np.dtype(np.float32))
-    total = time.perf_counter() - t0
-    per_step = total / args.steps
-    value = chain_bytes(side) / per_step / 1e9
+        oracle.evaluate(root, F32)
+    per_step = (time.perf_counter() - t0) / args.steps
+    value = workloads.chain_bytes(side) / per_step / 1e9
     sample = ("the same chain on x=[%d,%d] (2^%d elements) per step; the reference's evaluator "
-              "is single-threaded by construction" % (side, side, args.ref_log2n))
+              "is single-threaded by construction (no threads, SIMD or BLAS: SURVEY.md 2.2), so "
+              "one core is all it can use" % (side, side, args.ref_log2n))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "elementwise chain add(mul(exp(x),extend(b)),permute(x)), fp32, "
-                               "bounded CPU sample", "sample_elements": side * side,
+        "config": {"workload": "elementwise chain add(mul(exp(x),extend(b,1,{D})),permute(x,{1,0})), fp32, "
+                               "bounded CPU sample of x=[16384,16384]", "sample_elements": side * side,
                    "full_elements": 1 << args.log2n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -186,7 +187,108 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-# ---- own arm ------------------------------------------------------------------------
+# ---- own arm ------------------------------------------------------------------------------
+
+class Timer:
+    """CUDA events on the evaluator's stream + barrier / max over ranks"""
+
+    def __init__(self, llo, capi, dist, torch):
+        self.llo = llo
+        self.ctx = capi.Context(handle=llo.context())
+        self.dist = dist
+        self.torch = torch
+        self.start, self.stop = self.ctx.event(), self.ctx.event()
+
+    def barrier(self):
+        self.llo.sync()
+        if self.dist is not None:
+            self.torch.cuda.synchronize()
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.dist is None:
+            return ms
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps, warmup):
+        """ms per step of `fn`, max over ranks; also returns the launches"""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        launches0 = self.llo.launch_count()
+        self.ctx.record(self.start)
+        for _ in range(steps):
+            fn()
+        self.ctx.record(self.stop)
+        ms = self.ctx.elapsed_ms(self.start, self.stop)
+        self.barrier()
+        launches = self.llo.launch_count() - launches0
+        return self.max_over_ranks(ms) / steps, launches
+
+
+def side_workloads(args, timer, age, llo, rank, world):
+    """BASELINE.json configs 3-5 (reported beside the headline)"""
+    out = {}
+    hbm_peak, _ = measured_peaks()
+    steps, warm = max(3, min(args.steps, 10)), 3
+    if world == 1 and not args.skip_side:
+        # config 3: reductions of [D, D], deterministic tree order
+        side = 1 << (args.log2n // 2)
+        x = np.random.default_rng(4).uniform(0.0, 1.0, (side, side)).astype(np.float32)
+        vx = llo.variable(x, "x")
+        nbytes = 4 * side * side
+        cases = {
+            "reduce_sum_cols": age.reduce_sum(vx, 1),                      # keeps the fastest dim
+            "reduce_max_cols": age.reduce_max(vx, 1),
+            "reduce_sum_all": age.reduce_sum0(vx),
+            "reduce_max_all": age.reduce_max0(vx),
+            "reduce_sum_rows": age.reduce_sum(age.permute(vx, [1, 0]), 1),  # contiguous rows, permute fused
+            "reduce_max_rows": age.reduce_max(age.permute(vx, [1, 0]), 1),
+        }
+        for name, root in cases.items():
+            ms, launches = timer.timed(lambda r=root: llo.evaluate_device(r, F32), steps, warm)
+            gbps = nbytes / ms / 1e6
+            out[name] = {"GBps": gbps, "ms": ms, "frac_of_measured_hbm": gbps / hbm_peak,
+                         "launches_per_eval": launches // steps}
+        del vx, x, cases
+        # config 4: matmul fp32 8192^3 on the FFMA pipe (exact path)
+        m = args.matmul
+        a = np.random.default_rng(5).uniform(-1, 1, (m, m)).astype(np.float32)
+        b = np.random.default_rng(6).uniform(-1, 1, (m, m)).astype(np.float32)
+        va, vb = llo.variable(a, "a"), llo.variable(b, "b")
+        root = age.matmul(va, vb)
+        ms, launches = timer.timed(lambda: llo.evaluate_device(root, F32), max(3, steps // 2), 2)
+        peak, src = ffma_peak()
+        tf = 2.0 * m ** 3 / ms / 1e9
+        out["matmul_f32"] = {"TFLOPs": tf, "ms": ms, "mnk": [m, m, m], "frac_of_ffma_peak": tf / peak,
+                             "ffma_peak_TFLOPs": peak, "peak_source": src,
+                             "launches_per_eval": launches // max(3, steps // 2)}
+        del va, vb, a, b, root
+    if not args.skip_mlp:
+        # config 5: MLP gradient evaluation, batch sharded over the ranks
+        from cortenn_b200.sharded import BatchShardedExecutor
+        batch = args.mlp_batch
+        X, Y, params = workloads.mlp_data(batch)
+        ex = BatchShardedExecutor(batch, rank=rank, world=world)
+        loss, pvars, _ = workloads.mlp_graph(age, llo, ex.shard(X), ex.shard(Y), params, global_batch=batch)
+        del X, Y
+
+        def grad_eval():
+            ex.grad_eval_device(loss, pvars, F32)
+        ms, launches = timer.timed(grad_eval, steps, warm)
+        flops = workloads.mlp_flops(batch)
+        peak, _ = ffma_peak()
+        out["mlp_grad_eval"] = {
+            "grad_evals_per_s": 1e3 / ms, "ms": ms, "batch": batch, "rows_per_rank": ex.local_rows(),
+            "gemm_TFLOPs_all_ranks": flops / ms / 1e9,
+            "frac_of_ffma_peak": flops / ms / 1e9 / (peak * world),
+            "allreduce_bytes": 4 * 1863690, "launches_per_eval": launches // steps,
+            "scaling": "strong (batch 65536 split over the ranks; NCCL allreduce of the packed gradients)"}
+    return out
+
 
 def run_own(args, rank, local_rank, world):
     os.environ.setdefault("LLO_CUDA_DEVICE", str(local_rank))
@@ -202,70 +304,52 @@ def run_own(args, rank, local_rank, world):
     from cortenn_b200 import age, capi, llo
     if not llo.available():
         raise RuntimeError("bench.py: no usable B200 and there is no CPU fallback")
-    ctx = capi.Context(handle=llo.context())
-
-    def barrier():
-        llo.sync()
-        if dist is not None:
-            torch.cuda.synchronize()
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if dist is None:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    timer = Timer(llo, capi, dist, torch)
 
     side = 1 << (args.log2n // 2)
-    f32 = np.dtype(np.float32)
-    x, b = chain_inputs(side, seed_x=2 + rank)
-    vx, vb, root = chain_graph(age, llo, x, b)
-    nbytes = chain_bytes(side)
+    x, b = workloads.chain_inputs(side, seed_x=2 + rank)
+    vx, vb, root = workloads.chain_graph(age, llo, x, b)
+    nbytes = workloads.chain_bytes(side)
+    warmup = max(args.warmup, 3)
 
     # ---- value: inputs resident in HBM, device-timed --------------------------
-    for _ in range(max(args.warmup, 3)):
-        res = llo.evaluate_device(root, f32)
-    del res
-    barrier()
+    for _ in range(warmup):
+        llo.evaluate_device(root, F32)
+    timer.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = llo.launch_count()
-    start, stop = ctx.event(), ctx.event()
-    ctx.record(start)
-    for _ in range(args.steps):
-        res = llo.evaluate_device(root, f32)
-    ctx.record(stop)
-    ms_total = ctx.elapsed_ms(start, stop)
-    barrier()
-    launches = llo.launch_count() - launches0
+    ms_step, launches = timer.timed(lambda: llo.evaluate_device(root, F32), args.steps, 0)
     clocks = sampler.stop() if rank == 0 else {}
-    ms_total = max_over_ranks(ms_total)
-    ms_step = ms_total / args.steps
     value = world * nbytes / ms_step / 1e6
-    del res
 
-    # ---- e2e: host buffers in, host buffer out, copies inside the timed region --
+    # ---- e2e: pinned host buffers in, host buffer out, copies inside the timed region --
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    llo.evaluate(root, f32)  # warm the staging buffers
-    barrier()
-    ctx.record(start)
-    for _ in range(e2e_steps):
-        vx.assign(x)                     # host -> pinned -> device at the next use
-        out = llo.evaluate(root, f32)    # device -> host numpy
-    ctx.record(stop)
-    e2e_ms = max_over_ranks(ctx.elapsed_ms(start, stop)) / e2e_steps
+    xp = llo.pinned_empty(list(x.shape), F32)
+    xp[...] = x
+    vx.assign(xp)
+    llo.evaluate(root, F32)  # warm the staging pool
+    timer.barrier()
+    holder = {}
+
+    def e2e_step():
+        vx.assign(xp)                             # pinned host -> device (DMA)
+        holder["out"] = llo.evaluate(root, F32)   # device -> pinned host numpy
+    e2e_ms, _ = timer.timed(e2e_step, e2e_steps, 1)
+    out = holder["out"]
     e2e = {"value": world * nbytes / e2e_ms / 1e6, "unit": UNIT,
            "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(out.nbytes),
-           "steps": e2e_steps, "ms_per_step": e2e_ms}
-    del out
+           "steps": e2e_steps, "ms_per_step": e2e_ms,
+           "path": "Variable.assign(pinned ndarray) + llo.evaluate -> ndarray, every step"}
+    del out, holder, xp
 
     peak, peak_src = measured_peaks()
+    per_eval = max(1, launches // args.steps)
     roofline = {"bound": "hbm", "achieved": nbytes / ms_step / 1e6, "peak": peak, "unit": "GB/s",
                 "frac": nbytes / ms_step / 1e6 / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "whole step (%d launch(es) per evaluation)" % (launches // args.steps)}
+                "frac_of_nominal_8TBs": nbytes / ms_step / 1e6 / 8000.0,
+                "kernel": "vm_tile_kernel<float> (the whole step is %d launch per evaluation)" % per_eval,
+                "algorithmic_bytes_per_launch": nbytes}
     traffic_path = os.path.join(ROOT, "profiles", "chain_traffic.json")
     if os.path.exists(traffic_path):
         with open(traffic_path) as fh:
@@ -274,29 +358,37 @@ def run_own(args, rank, local_rank, world):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cside = 1 << (args.cpu_log2n // 2)
-        sec, gbps = cpu_chain(cside, 2)
+        sec, gbps = cpu_chain(cside, args.cpu_repeats)
         cpu_baseline = {"value": gbps, "unit": UNIT, "cores": 1, "kind": "port",
                         "sample": "oracle (CPU restatement of llo::Evaluator) on the same chain at "
-                                  "x=[%d,%d] (2^%d elements), %.2f s per evaluation, single thread "
-                                  "like the reference" % (cside, cside, args.cpu_log2n, sec)}
+                                  "x=[%d,%d] (2^%d of the 2^%d elements), %d evaluations of %.2f s, "
+                                  "single thread like the reference; host has %d cores"
+                                  % (cside, cside, args.cpu_log2n, args.log2n, args.cpu_repeats, sec,
+                                     os.cpu_count() or 0)}
+
+    del vx, vb, root, x, b
+    side_results = side_workloads(args, timer, age, llo, rank, world)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "elementwise chain add(mul(exp(x),extend(b,1,{D})),permute(x,{1,0})), "
                                    "x=[%d,%d] fp32 (2^%d elements), ade graph via age API -> llo.evaluate_device"
                                    % (side, side, args.log2n),
                        "bytes_per_step": nbytes,
-                       "l2": "inputs larger than L2 (x is %d MiB, L2 is 126 MB)" % (x.nbytes >> 20),
-                       "multi_gpu": "independent replicas per rank (single-operator configs do not shard)"},
+                       "l2": "inputs larger than L2 (x is %d MiB, L2 is 126 MB)" % ((4 * side * side) >> 20),
+                       "multi_gpu": "independent replicas per rank (single-operator configs do not shard); "
+                                    "the batch-sharded MLP is under workloads.mlp_grad_eval"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "workloads": side_results,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
+        timer.barrier()
+        llo.comm_destroy()
         dist.destroy_process_group()
 
 
@@ -308,9 +400,14 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--log2n", type=int, default=28, help="elements of the chain (2^k, k even)")
     ap.add_argument("--cpu-log2n", type=int, default=22, help="elements of the CPU-baseline sample")
+    ap.add_argument("--cpu-repeats", type=int, default=10)
     ap.add_argument("--ref-log2n", type=int, default=20, help="elements per step of the reference arm")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--matmul", type=int, default=8192)
+    ap.add_argument("--mlp-batch", type=int, default=65536)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-side", action="store_true", help="skip the reduce / matmul workloads")
+    ap.add_argument("--skip-mlp", action="store_true")
     args = ap.parse_args()
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)

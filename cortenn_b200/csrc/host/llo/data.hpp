@@ -188,6 +188,11 @@ private:
 
 	mutable std::shared_ptr<char> host_;
 
+	/// True while the newest bytes only exist in the device mirror (an
+	/// assignment uploads straight from the caller's buffer); the host copy
+	/// is refreshed on demand
+	mutable bool host_stale_ = false;
+
 	/// One element's bytes while the leaf is a known constant
 	std::vector<char> fill_;
 

@@ -1,4 +1,5 @@
 #include <cstdlib>
+#include <map>
 #include <mutex>
 
 #include "llo/data.hpp"
@@ -76,16 +77,64 @@ std::shared_ptr<char> alloc (size_t nbytes)
 
 static const size_t pin_threshold = 1 << 16;
 
+/// Pinned blocks are expensive to create (cudaHostAlloc maps and locks every
+/// page), so released blocks are kept for the next request of the same size
+struct PinnedPool
+{
+	std::mutex lock_;
+	std::multimap<size_t,void*> free_;
+	size_t cached_ = 0;
+	static constexpr size_t cap_ = (size_t) 8 << 30;
+
+	void* take (size_t nbytes)
+	{
+		std::lock_guard<std::mutex> guard(lock_);
+		auto it = free_.find(nbytes);
+		if (free_.end() == it)
+		{
+			return nullptr;
+		}
+		void* ptr = it->second;
+		free_.erase(it);
+		cached_ -= nbytes;
+		return ptr;
+	}
+
+	bool give (size_t nbytes, void* ptr)
+	{
+		std::lock_guard<std::mutex> guard(lock_);
+		if (cached_ + nbytes > cap_)
+		{
+			return false;
+		}
+		free_.emplace(nbytes, ptr);
+		cached_ += nbytes;
+		return true;
+	}
+};
+
+static PinnedPool& pinned_pool (void)
+{
+	static PinnedPool* pool = new PinnedPool(); // outlives every array
+	return *pool;
+}
+
 std::shared_ptr<char> host_alloc (size_t nbytes)
 {
 	if (nbytes >= pin_threshold && available())
 	{
 		llo_cuda_ctx* c = ctx();
-		void* ptr = nullptr;
-		if (LLO_OK == llo_cuda_host_alloc(c, nbytes, &ptr))
+		void* ptr = pinned_pool().take(nbytes);
+		if (nullptr != ptr || LLO_OK == llo_cuda_host_alloc(c, nbytes, &ptr))
 		{
 			return std::shared_ptr<char>((char*) ptr,
-				[c](char* p) { llo_cuda_host_free(c, p); });
+				[c, nbytes](char* p)
+				{
+					if (false == pinned_pool().give(nbytes, p))
+					{
+						llo_cuda_host_free(c, p);
+					}
+				});
 		}
 	}
 	return std::shared_ptr<char>((char*) std::malloc(std::max<size_t>(nbytes, 1)),
@@ -156,10 +205,11 @@ Variable::Variable (const Variable& other) :
 	label_(other.label_), fill_(other.fill_),
 	shape_(other.shape_), dtype_(other.dtype_)
 {
-	if (nullptr != other.host_)
+	if (nullptr != other.host_ || other.host_stale_)
 	{
+		const void* src = other.data(); // refreshes a stale host copy
 		host_ = device::host_alloc(nbytes());
-		std::memcpy(host_.get(), other.host_.get(), nbytes());
+		std::memcpy(host_.get(), src, nbytes());
 	}
 }
 
@@ -172,10 +222,12 @@ Variable& Variable::operator = (const Variable& other)
 		shape_ = other.shape_;
 		dtype_ = other.dtype_;
 		host_ = nullptr;
-		if (nullptr != other.host_)
+		host_stale_ = false;
+		if (nullptr != other.host_ || other.host_stale_)
 		{
+			const void* src = other.data();
 			host_ = device::host_alloc(nbytes());
-			std::memcpy(host_.get(), other.host_.get(), nbytes());
+			std::memcpy(host_.get(), src, nbytes());
 		}
 		++version_;
 		mirrors_.clear();
@@ -197,18 +249,59 @@ Variable& Variable::operator = (GenericRef data)
 			"(external) and %s (internal)",
 			age::name_type(data.dtype_).c_str(), age::name_type(dtype_).c_str());
 	}
+	fill_.clear();
+	++version_;
+	if (device::available())
+	{
+		// upload straight from the caller's buffer (one pass; DMA when the
+		// buffer is pinned); the host copy is refreshed only if asked for
+		std::shared_ptr<char> raw;
+		for (Mirror& m : mirrors_)
+		{
+			if (m.dtype_ == dtype_)
+			{
+				raw = m.data_;
+			}
+		}
+		if (nullptr == raw)
+		{
+			raw = device::alloc(nbytes());
+		}
+		device::check(llo_cuda_h2d(device::ctx(), raw.get(), data.data_,
+			nbytes()));
+		mirrors_.clear(); // converted mirrors are out of date
+		mirrors_.push_back(Mirror{dtype_, version_, raw});
+		host_stale_ = true;
+		return *this;
+	}
 	if (nullptr == host_)
 	{
 		host_ = device::host_alloc(nbytes());
 	}
-	fill_.clear();
 	std::memcpy(host_.get(), data.data_, nbytes());
-	++version_;
 	return *this;
 }
 
 void Variable::materialize (void) const
 {
+	if (host_stale_)
+	{
+		if (nullptr == host_)
+		{
+			host_ = device::host_alloc(nbytes());
+		}
+		for (Mirror& m : mirrors_)
+		{
+			if (m.dtype_ == dtype_ && m.version_ == version_)
+			{
+				device::check(llo_cuda_d2h(device::ctx(), host_.get(),
+					m.data_.get(), nbytes()));
+				host_stale_ = false;
+				return;
+			}
+		}
+		logs::fatal("variable lost its device mirror while the host copy was stale");
+	}
 	if (nullptr != host_)
 	{
 		return;

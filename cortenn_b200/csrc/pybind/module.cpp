@@ -133,6 +133,18 @@ static age::_GENERATED_DTYPE eval_dtype (py::dtype dtype)
 	return exact_dtype(dtype, "evaluate");
 }
 
+/// numpy array over a host block the array keeps alive: the result's pinned
+/// mirror is handed to numpy as is (the reference lets numpy copy the buffer,
+/// llo/python/llo.cpp:143-146; the array is the block's only owner either way)
+static py::array wrap_host (py::dtype dtype, std::vector<py::ssize_t> pshape,
+	std::shared_ptr<char> block)
+{
+	auto holder = new std::shared_ptr<char>(block);
+	py::capsule base(holder, [](void* p)
+		{ delete static_cast<std::shared_ptr<char>*>(p); });
+	return py::array(dtype, pshape, block.get(), base);
+}
+
 static py::array evaluate (ade::TensptrT tens, py::dtype dtype)
 {
 	age::_GENERATED_DTYPE ctype = eval_dtype(dtype);
@@ -142,8 +154,7 @@ static py::array evaluate (ade::TensptrT tens, py::dtype dtype)
 		gdata = llo::eval(tens, ctype);
 	}
 	auto pshape = c2pshape(gdata.shape_);
-	// no base object: numpy copies the buffer (as in the reference)
-	return py::array(dtype, pshape, gdata.data_.get());
+	return wrap_host(dtype, pshape, gdata.data_);
 }
 
 /// Device-resident result handle
@@ -348,6 +359,17 @@ PYBIND11_MODULE(_C, m)
 				auto pshape = pyllo::c2pshape(self.data_.shape_);
 				return py::array(dtype, pshape, self.data_.fetch());
 			});
+	llo_m.def("pinned_empty", [](std::vector<py::ssize_t> shape, py::dtype dtype)
+		{
+			size_t n = (size_t) dtype.itemsize();
+			for (py::ssize_t d : shape)
+			{
+				n *= (size_t) d;
+			}
+			return pyllo::wrap_host(dtype, shape, llo::device::host_alloc(n));
+		}, "uninitialised numpy array in page-locked host memory: "
+		"Variable.assign from it and evaluate() move data by DMA",
+		py::arg("shape"), py::arg("dtype") = py::dtype::of<double>());
 	llo_m.def("evaluate_device", [](T tens, py::dtype dtype)
 		{
 			age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);
