@@ -46,6 +46,7 @@ struct PlanStats
 	size_t gemms_ = 0;        // contractions lowered to GEMM
 	size_t generic_ = 0;      // functors run through age::op_exec
 	size_t simplified_ = 0;   // algebraic rewrites applied
+	size_t shared_ = 0;       // plan nodes merged with a structurally equal one
 };
 
 /// Evaluate `root` as `dtype` on the device; the result stays in HBM

@@ -358,6 +358,92 @@ struct Plan
 		n->shape_ = shape;
 		n->dtype_ = dtype;
 		++stats_.consts_;
+		return intern(n);
+	}
+
+	// ---- common sub-expression sharing ---------------------------------------
+	//
+	// llo::derive builds one gradient graph per target; the graphs of
+	// different targets (and the paths inside one graph) repeat the same
+	// backward chains as distinct ade nodes.  Plan nodes are therefore
+	// hash-consed on their structure, so every distinct computation is
+	// planned - and run - once per evaluation.
+
+	template <typename V>
+	static void put (std::string& key, const V& v)
+	{
+		key.append((const char*) &v, sizeof(V));
+	}
+
+	static void put_view (std::string& key, const CoordView& v)
+	{
+		for (int j = 0; j < R; ++j)
+		{
+			put(key, v.t_[j].src_);
+			put(key, v.t_[j].scale_);
+			put(key, v.t_[j].offset_);
+		}
+	}
+
+	static void put_shape (std::string& key, const ade::Shape& shape)
+	{
+		for (int j = 0; j < R; ++j)
+		{
+			put(key, shape.at(j));
+		}
+	}
+
+	PNode* intern (PNode* n)
+	{
+		if (n->has_rand_)
+		{
+			return n; // random draws are never shared
+		}
+		std::string key;
+		put(key, n->kind_);
+		put(key, n->opcode_);
+		put(key, n->dtype_);
+		put_shape(key, n->shape_);
+		put(key, n->leaf_);
+		if (Kind::CONST == n->kind_)
+		{
+			put(key, n->value_);
+		}
+		if (Kind::REDUCE == n->kind_)
+		{
+			put_shape(key, n->argshape_);
+			put_view(key, n->kept_);
+			for (int dim : n->fold_)
+			{
+				put(key, dim);
+			}
+		}
+		for (const PArg& a : n->args_)
+		{
+			put(key, a.node_);
+			put_view(key, a.view_);
+			if (Kind::GENERIC == n->kind_)
+			{
+				put(key, a.push_);
+				a.coorder_->access([&](const ade::MatrixT& m)
+				{
+					for (int i = 0; i <= R; ++i)
+					{
+						for (int j = 0; j <= R; ++j)
+						{
+							put(key, m[i][j]);
+						}
+					}
+				});
+			}
+		}
+		auto it = interned_.find(key);
+		if (interned_.end() != it)
+		{
+			++stats_.shared_;
+			return it->second;
+		}
+		interned_.emplace(std::move(key), n);
 		return n;
 	}
 
@@ -407,7 +493,7 @@ struct Plan
 		n->leaf_ = leaf;
 		n->shape_ = leaf->shape();
 		n->dtype_ = dtype;
-		return n;
+		return intern(n);
 	}
 
 	/// value of a leaf constant after the reference's leaf conversion
@@ -469,7 +555,7 @@ struct Plan
 		}
 		n->has_rand_ = n->has_rand_ || is_rand(n->opcode_);
 		++stats_.generic_;
-		return n;
+		return intern(n);
 	}
 
 	PNode* build_functor (ade::iFunctor* func, DT dtype)
@@ -553,7 +639,7 @@ struct Plan
 		n->args_.push_back(resolve(child, CoordView::identity(),
 			child->shape_));
 		n->has_rand_ = child->has_rand_;
-		return n;
+		return intern(n);
 	}
 
 	PNode* make_view (const ade::Shape& shape, const PArg& arg, DT dtype)
@@ -574,7 +660,7 @@ struct Plan
 		n->args_.push_back(arg);
 		n->has_rand_ = arg.node_->has_rand_;
 		++stats_.views_;
-		return n;
+		return intern(n);
 	}
 
 	static bool is_const (const PArg& a, double v)
@@ -668,7 +754,7 @@ struct Plan
 		{
 			n->has_rand_ = n->has_rand_ || a.node_->has_rand_;
 		}
-		return n;
+		return intern(n);
 	}
 
 	// ---- use counting and inlining costs --------------------------------------
@@ -1152,6 +1238,7 @@ struct Plan
 	PlanStats stats_;
 	std::vector<std::unique_ptr<PNode>> arena_;
 	std::map<std::pair<ade::iTensor*,int>,PNode*> memo_;
+	std::unordered_map<std::string,PNode*> interned_;
 };
 
 static thread_local PlanStats last_stats;

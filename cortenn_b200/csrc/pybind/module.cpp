@@ -504,6 +504,7 @@ PYBIND11_MODULE(_C, m)
 			out["gemms"] = st.gemms_;
 			out["generic"] = st.generic_;
 			out["simplified"] = st.simplified_;
+			out["shared"] = st.shared_;
 			return out;
 		});
 	llo_m.def("set_option", &llo::set_option);
