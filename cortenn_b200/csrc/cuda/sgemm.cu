@@ -27,6 +27,7 @@
 ///   Out-of-range parts of edge tiles are zero-filled by TMA and add 0.
 ///
 
+#include <algorithm>
 #include <utility>
 
 #include <cuda.h>
@@ -67,6 +68,10 @@ struct SgemmArgs
 	uint32_t tiles_m;
 	uint32_t tiles_n;
 	uint32_t vec_store; // C rows allow aligned 128-bit stores
+	// split-K: CTA (tile, y) reduces k-tiles [y * kt_per_split, +kt_per_split)
+	// into the partial product C + y * split_stride
+	uint32_t kt_per_split;
+	int64_t split_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32 (const void* p)
@@ -171,7 +176,8 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 	uint32_t gsize = min(args.tiles_m - first_m, GROUP);
 	uint32_t tile_m = first_m + (bid % per_group) % gsize;
 	uint32_t tile_n = (bid % per_group) / gsize;
-	uint32_t ktiles = (args.K + BK - 1) / BK;
+	uint32_t kt_begin = blockIdx.y * args.kt_per_split;
+	uint32_t ktiles = min((args.K + BK - 1) / BK - kt_begin, args.kt_per_split);
 
 	int warp = threadIdx.x >> 5;
 	int lane = threadIdx.x & 31;
@@ -181,7 +187,7 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 	{
 		uint32_t s = kt % STAGES;
 		mbar_expect_tx(&full[s], STAGE_BYTES);
-		int k0 = (int) (kt * BK);
+		int k0 = (int) ((kt_begin + kt) * BK);
 		if (AK)
 		{
 			tma_load_2d(tiles_a + s * A_STAGE_FLOATS, &map_a, &full[s],
@@ -413,7 +419,8 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 		{
 			continue;
 		}
-		float* crow = args.C + (int64_t) m * args.c_rs;
+		float* crow = args.C + (int64_t) blockIdx.y * args.split_stride +
+			(int64_t) m * args.c_rs;
 		if (BKC)
 		{
 #pragma unroll
@@ -512,21 +519,80 @@ bool tma_operand_ok (const float* base, int64_t lead)
 		lead < (1ll << 38);
 }
 
+/// dst[r * dst_ld + c] = src[r * src_ld + c]: re-pitch an operand whose rows
+/// TMA cannot address (pitch not a multiple of 16 bytes, e.g. the 10-wide
+/// last layer of the MLP)
+__global__ void __launch_bounds__(256)
+repitch_kernel (float* __restrict__ dst, const float* __restrict__ src,
+	uint64_t rows, uint32_t cols, int64_t src_ld, int64_t dst_ld)
+{
+	uint64_t i = (uint64_t) blockIdx.x * 256 + threadIdx.x;
+	uint64_t r = i / cols;
+	uint32_t c = (uint32_t) (i - r * cols);
+	if (r < rows)
+	{
+		dst[r * dst_ld + c] = __ldg(src + r * src_ld + c);
+	}
+}
+
+/// C[m * c_rs + n] = sum over s (ascending) of part[s][m][n]: the fixed-order
+/// second pass of split-K
+__global__ void __launch_bounds__(256)
+splitk_fold_kernel (float* __restrict__ C, int64_t c_rs,
+	const float* __restrict__ part, uint32_t M, uint32_t N, int64_t ld,
+	int64_t split_stride, uint32_t splits)
+{
+	uint64_t i = (uint64_t) blockIdx.x * 256 + threadIdx.x;
+	uint64_t m = i / N;
+	uint32_t n = (uint32_t) (i - m * N);
+	if (m >= M)
+	{
+		return;
+	}
+	const float* p = part + m * ld + n;
+	float acc = __ldcs(p);
+	for (uint32_t s = 1; s < splits; ++s)
+	{
+		acc = __fadd_rn(acc, __ldcs(p + (int64_t) s * split_stride));
+	}
+	C[m * c_rs + n] = acc;
+}
+
 template <bool AK, bool BKC>
 int launch_variant (llo_cuda_ctx* ctx, const CUtensorMap& ma,
-	const CUtensorMap& mb, const SgemmArgs& args)
+	const CUtensorMap& mb, const SgemmArgs& args, uint32_t splits)
 {
-	static bool configured = false;
-	if (false == configured)
-	{
-		LLO_CUDA_TRY(cudaFuncSetAttribute(sgemm_tma_kernel<AK,BKC>,
-			cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM_BYTES));
-		configured = true;
-	}
-	uint64_t blocks = (uint64_t) args.tiles_m * args.tiles_n;
-	sgemm_tma_kernel<AK,BKC><<<(unsigned) blocks, THREADS, SMEM_BYTES,
+	LLO_CUDA_TRY(cudaFuncSetAttribute(sgemm_tma_kernel<AK,BKC>,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM_BYTES));
+	dim3 grid(args.tiles_m * args.tiles_n, splits);
+	sgemm_tma_kernel<AK,BKC><<<grid, THREADS, SMEM_BYTES,
 		ctx->stream>>>(ma, mb, args);
 	return launched(ctx, "sgemm_tma_kernel");
+}
+
+/// Make `base` (rows x cols, row pitch `lead`) addressable by TMA, copying it
+/// to a 16-byte pitched scratch buffer when it is not
+int tma_ready (llo_cuda_ctx* ctx, Scratch& scratch, const float*& base,
+	int64_t& lead, uint64_t rows, uint64_t cols)
+{
+	if (tma_operand_ok(base, lead))
+	{
+		return LLO_OK;
+	}
+	if (lead < (int64_t) cols && rows > 1)
+	{
+		return fail(LLO_ERR_FATAL, "gemm operand rows overlap");
+	}
+	int64_t ld = (int64_t) ((cols + 3) / 4 * 4);
+	void* copy = nullptr;
+	LLO_TRY(scratch.get(&copy, (size_t) rows * ld * sizeof(float)));
+	uint64_t total = rows * cols;
+	repitch_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(
+		(float*) copy, base, rows, (uint32_t) cols, lead, ld);
+	LLO_TRY(launched(ctx, "repitch_kernel"));
+	base = (const float*) copy;
+	lead = ld;
+	return LLO_OK;
 }
 
 }
@@ -554,11 +620,19 @@ int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p0, float* C,
 		p.a_rs = a_rs; p.a_cs = a_cs; p.b_rs = b_rs; p.b_cs = b_cs;
 		std::swap(p.c_rs, p.c_cs);
 	}
-	if (p.M < 32 || p.N < 32 || p.K < 32 ||
+	if (p.M * p.N * p.K < 32768 ||
 		p.M >= (1ull << 31) || p.N >= (1ull << 31) || p.K >= (1ull << 31))
 	{
-		return LLO_OK; // skinny / tiny / huge problems take the generic kernel
+		return LLO_OK; // tiny / huge problems take the generic kernel
 	}
+	if (nullptr == tensor_map_encoder())
+	{
+		return LLO_OK;
+	}
+	// a 1-long dimension has no meaningful stride: pick the contiguous form
+	if (1 == p.K) { p.a_cs = 1; p.b_rs = 1; }
+	if (1 == p.M) { p.a_rs = (1 == p.a_cs) ? (int64_t) p.K : 1; }
+	if (1 == p.N) { p.b_cs = (1 == p.b_rs) ? (int64_t) p.K : 1; p.c_cs = 1; }
 	bool ak = (1 == p.a_cs);
 	bool bk = (1 == p.b_rs);
 	if ((false == ak && 1 != p.a_rs) || (false == bk && 1 != p.b_cs))
@@ -567,10 +641,13 @@ int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p0, float* C,
 	}
 	int64_t lead_a = ak ? p.a_rs : p.a_cs;
 	int64_t lead_b = bk ? p.b_cs : p.b_rs;
-	if (false == tma_operand_ok(A, lead_a) || false == tma_operand_ok(B, lead_b))
+	if (lead_a <= 0 || lead_b <= 0)
 	{
-		return LLO_OK;
+		return LLO_OK; // broadcast or mirrored operands
 	}
+	Scratch scratch(ctx);
+	LLO_TRY(tma_ready(ctx, scratch, A, lead_a, ak ? p.M : p.K, ak ? p.K : p.M));
+	LLO_TRY(tma_ready(ctx, scratch, B, lead_b, bk ? p.N : p.K, bk ? p.K : p.N));
 	CUtensorMap ma, mb;
 	bool ok = ak ?
 		make_map(ma, A, p.K, p.M, lead_a, BK, BM, true) :
@@ -583,28 +660,88 @@ int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p0, float* C,
 		return LLO_OK;
 	}
 	SgemmArgs args;
-	args.C = C;
-	args.c_rs = p.c_rs;
 	args.M = (uint32_t) p.M;
 	args.N = (uint32_t) p.N;
 	args.K = (uint32_t) p.K;
 	args.tiles_m = (uint32_t) ((p.M + BM - 1) / BM);
 	args.tiles_n = (uint32_t) ((p.N + BN - 1) / BN);
-	int64_t need = bk ? 2 : 4;
-	args.vec_store = (0 == ((uintptr_t) C & (uintptr_t) (need * 4 - 1)) &&
-		0 == p.c_rs % need) ? 1 : 0;
-	if ((uint64_t) args.tiles_m * args.tiles_n >= 0x7fffffffull)
+	uint64_t tiles = (uint64_t) args.tiles_m * args.tiles_n;
+	if (tiles >= 0x7fffffffull)
 	{
 		return LLO_OK;
 	}
+	// split-K: when the output has fewer tiles than the chip has SMs, the
+	// k-tiles of every output tile are spread over `splits` CTAs and the
+	// partial products are summed in split order by a second pass
+	uint32_t ktiles = (uint32_t) ((p.K + BK - 1) / BK);
+	uint32_t splits = 1;
+	if (tiles * 2 <= (uint64_t) ctx->sm_count && ktiles >= 16)
+	{
+		// pick the split count whose grid fills whole waves of SMs best
+		// (ties: fewer splits), between ~1 and ~4 waves
+		uint64_t sms = (uint64_t) ctx->sm_count;
+		uint64_t most = std::min<uint64_t>(ktiles / 8, 64);
+		uint64_t lo = std::max<uint64_t>(2, sms / tiles);
+		uint64_t hi = std::min<uint64_t>(most, (4 * sms + tiles - 1) / tiles);
+		double best = 0;
+		for (uint64_t cand = lo; cand <= hi; ++cand)
+		{
+			uint64_t ctas = tiles * cand;
+			uint64_t waves = (ctas + sms - 1) / sms;
+			double fill = (double) ctas / (double) (waves * sms);
+			if (fill > best + 0.02)
+			{
+				best = fill;
+				splits = (uint32_t) cand;
+			}
+		}
+	}
+	args.kt_per_split = (ktiles + splits - 1) / splits;
+	splits = (ktiles + args.kt_per_split - 1) / args.kt_per_split;
+	int64_t need = bk ? 2 : 4;
+	float* part = nullptr;
+	int64_t part_ld = 0;
+	if (splits > 1)
+	{
+		part_ld = (int64_t) ((p.N + 3) / 4 * 4);
+		void* ws = nullptr;
+		LLO_TRY(scratch.get(&ws, (size_t) splits * p.M * part_ld * sizeof(float)));
+		part = (float*) ws;
+		args.C = part;
+		args.c_rs = part_ld;
+		args.split_stride = (int64_t) p.M * part_ld;
+		args.vec_store = 1;
+	}
+	else
+	{
+		args.C = C;
+		args.c_rs = p.c_rs;
+		args.split_stride = 0;
+		args.vec_store = (0 == ((uintptr_t) C & (uintptr_t) (need * 4 - 1)) &&
+			0 == p.c_rs % need) ? 1 : 0;
+	}
 	handled = true;
+	int rc = LLO_OK;
 	if (ak)
 	{
-		return bk ? launch_variant<true,true>(ctx, ma, mb, args) :
-			launch_variant<true,false>(ctx, ma, mb, args);
+		rc = bk ? launch_variant<true,true>(ctx, ma, mb, args, splits) :
+			launch_variant<true,false>(ctx, ma, mb, args, splits);
 	}
-	return bk ? launch_variant<false,true>(ctx, ma, mb, args) :
-		launch_variant<false,false>(ctx, ma, mb, args);
+	else
+	{
+		rc = bk ? launch_variant<false,true>(ctx, ma, mb, args, splits) :
+			launch_variant<false,false>(ctx, ma, mb, args, splits);
+	}
+	LLO_TRY(rc);
+	if (splits > 1)
+	{
+		uint64_t total = p.M * p.N;
+		splitk_fold_kernel<<<(unsigned) ((total + 255) / 256), 256, 0,
+			ctx->stream>>>(C, p.c_rs, part, (uint32_t) p.M, (uint32_t) p.N,
+			part_ld, args.split_stride, splits);
+		LLO_TRY(launched(ctx, "splitk_fold_kernel"));
+	}
+	return LLO_OK;
 }
 
 }

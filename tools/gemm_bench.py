@@ -35,7 +35,9 @@ def check(ctx, dtype, precision):
     rng = np.random.default_rng(7)
     worst = 0.0
     sizes = [(128, 128, 32), (256, 128, 64), (200, 136, 100), (129, 260, 36), (64, 32, 1000),
-             (1000, 36, 64), (333, 444, 555), (32, 32, 32), (1024, 1024, 1024)]
+             (1000, 36, 64), (333, 444, 555), (32, 32, 32), (1024, 1024, 1024),
+             (4096, 10, 256), (512, 10, 8192), (4096, 256, 10), (100, 100, 10000), (1, 64, 1024),
+             (64, 1, 1024), (300, 200, 1), (784, 1024, 4096), (7, 5, 3000)]
     for (M, N, K) in sizes:
         A = rng.uniform(-1, 1, (M, K)).astype(dtype)
         B = rng.uniform(-1, 1, (K, N)).astype(dtype)
