@@ -185,6 +185,321 @@ vm_tile_kernel (const __grid_constant__ VmParams p)
 	}
 }
 
+// ---- tile launch for 4-byte types: cp.async staging, swizzled tiles ------------
+//
+// 64 x 64 tile.  The staged (transposed) input tile is copied as it lies in
+// memory, 16 bytes per cp.async, into smem [r0][p] (r0: output dim 0, p: the
+// input's contiguous direction) with the 16-byte chunk index XORed by
+// (r0 >> 2) & 7.  The compute phase reads it transposed: per warp
+// instruction 8 lanes x 4 consecutive r0 (one chunk column each, spread by
+// the XOR) times 4 lanes of consecutive p (the 4 words of one chunk): 32
+// distinct banks.  Chunk u of a thread: row p = 4 * quad + s, columns
+// 32 * half + 4 * l .. +4 with l = t & 7, s = (t >> 3) & 3, (quad, half)
+// from (warp, u).
+
+constexpr int VM_TS = 64;
+
+__device__ __forceinline__ void cp_async16 (void* smem_dst, const void* src,
+	int src_bytes)
+{
+	uint32_t dst = (uint32_t) __cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+		:: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+/// 32-bit form of rest_offset (the tile launch requires 32-bit addressing)
+__device__ __forceinline__ int32_t rest_offset32 (const VmParams& p,
+	const int64_t (&stride)[LLO_RANK], uint32_t brest)
+{
+	int32_t off = 0;
+	for (int d = 2; d < p.ndims; ++d)
+	{
+		uint32_t dim = (uint32_t) p.dims[d];
+		uint32_t q = brest / dim;
+		off += (int32_t) (brest - q * dim) * (int32_t) stride[d];
+		brest = q;
+	}
+	return off;
+}
+
+template <typename T>
+struct Tile4Loader
+{
+	using G = VmGeom<T>;
+
+	const VmParams& p;
+	const T* tiles;          // [slot][64][64], chunk-swizzled
+	uint32_t c0;             // output coordinates of chunk 0; chunk u sits at
+	uint32_t c1;             // (c0 + 32 * (u & 1), c1 + 4 * (u >> 1))
+	uint32_t dim0;
+	uint32_t dim1;
+	uint32_t brest;
+	bool full;               // the whole tile lies inside the output
+
+	__device__ __forceinline__ int valid (int u) const
+	{
+		if (full)
+		{
+			return 4;
+		}
+		uint32_t a = c0 + 32 * (u & 1);
+		if (c1 + 4 * (u >> 1) >= dim1 || a >= dim0)
+		{
+			return 0;
+		}
+		uint32_t left = dim0 - a;
+		return left < 4u ? (int) left : 4;
+	}
+
+	__device__ __forceinline__ void load (T (&x)[G::V], int k) const
+	{
+		const VmInput& in = p.in[k];
+		if (VM_IN_TILE == in.mode)
+		{
+			int l = threadIdx.x & 7;
+			int s = (threadIdx.x >> 3) & 3;
+			int quad = (threadIdx.x >> 5) * 2;   // of chunks 0/1; chunks 2/3: + 1
+			const T* tile = tiles + in.vec_ok * VM_TS * VM_TS +
+				4 * l * VM_TS + s;
+#pragma unroll
+			for (int u = 0; u < 4; ++u)
+			{
+				const T* src = tile + 32 * (u & 1) * VM_TS +
+					(((quad + (u >> 1)) ^ l) << 2);
+#pragma unroll
+				for (int e = 0; e < 4; ++e)
+				{
+					x[u * 4 + e] = src[e * VM_TS];
+				}
+			}
+			return;
+		}
+		const T* data = static_cast<const T*>(in.data);
+		int32_t s0 = (int32_t) in.stride[0];
+		int32_t s1 = (int32_t) in.stride[1];
+		int32_t off = (int32_t) in.offset + rest_offset32(p, in.stride, brest) +
+			(int32_t) c0 * s0 + (int32_t) c1 * s1;
+		if (1 == s0)
+		{
+			if (full && in.vec_ok)
+			{
+#pragma unroll
+				for (int u = 0; u < 4; ++u)
+				{
+					uint4 tmp = __ldg(reinterpret_cast<const uint4*>(
+						data + off + 32 * (u & 1) + 4 * (u >> 1) * s1));
+					const T* t = reinterpret_cast<const T*>(&tmp);
+#pragma unroll
+					for (int e = 0; e < 4; ++e)
+					{
+						x[u * 4 + e] = t[e];
+					}
+				}
+				return;
+			}
+#pragma unroll
+			for (int u = 0; u < 4; ++u)
+			{
+				load_chunk<T,4,false>(x + u * 4,
+					data + off + 32 * (u & 1) + 4 * (u >> 1) * s1,
+					in.vec_ok, valid(u));
+			}
+		}
+		else if (0 == s0)
+		{
+#pragma unroll
+			for (int u = 0; u < 4; u += 2)
+			{
+				// chunks u and u + 1 differ in dim 0 only: same element
+				T v = (valid(u) > 0 || valid(u + 1) > 0) ?
+					__ldg(data + off + 4 * (u >> 1) * s1) : T();
+#pragma unroll
+				for (int e = 0; e < 8; ++e)
+				{
+					x[u * 4 + e] = v;
+				}
+			}
+		}
+		else
+		{
+#pragma unroll
+			for (int u = 0; u < 4; ++u)
+			{
+				int ok = valid(u);
+				const T* src = data + off + 32 * (u & 1) * s0 + 4 * (u >> 1) * s1;
+#pragma unroll
+				for (int e = 0; e < 4; ++e)
+				{
+					x[u * 4 + e] = (e < ok) ? __ldg(src + e * s0) : T();
+				}
+			}
+		}
+	}
+};
+
+template <typename T, bool ALIGNED>
+__global__ void __launch_bounds__(VM_THREADS, 4)
+vm_tile4_kernel (const __grid_constant__ VmParams p)
+{
+	static_assert(4 == sizeof(T), "4-byte element types only");
+	using G = VmGeom<T>;
+	extern __shared__ __align__(16) unsigned char vm_smem[];
+	T* tiles = reinterpret_cast<T*>(vm_smem);
+	T* spill = tiles + p.nstaged * VM_TS * VM_TS;
+
+	// block -> (tile along dim 0, tile along dim 1, every other dim)
+	uint32_t per = p.tiles0 * p.tilesp;
+	uint32_t brest = blockIdx.x / per;
+	uint32_t b = blockIdx.x - brest * per;
+	uint32_t t0, tp;
+	if (p.mirror)
+	{
+		// tiles (i,j) and (j,i) get neighbouring block numbers, so an input
+		// that is read both straight and transposed (x and permute(x)) comes
+		// from DRAM once and from L2 the second time
+		uint32_t side = p.tiles0;
+		uint32_t off_diag = side * (side - 1);
+		if (b < off_diag)
+		{
+			uint32_t q = b >> 1; // pair (i < j), q = j (j - 1) / 2 + i
+			uint32_t j = (uint32_t) ((1.0f + sqrtf(1.0f + 8.0f * (float) q)) * 0.5f);
+			while (j * (j - 1) / 2 > q) { --j; }
+			while ((j + 1) * j / 2 <= q) { ++j; }
+			uint32_t i = q - j * (j - 1) / 2;
+			t0 = (b & 1) ? j : i;
+			tp = (b & 1) ? i : j;
+		}
+		else
+		{
+			t0 = tp = b - off_diag;
+		}
+	}
+	else
+	{
+		t0 = b % p.tiles0;
+		tp = b / p.tiles0;
+	}
+	uint32_t o0 = t0 * VM_TS;
+	uint32_t o1 = tp * VM_TS;
+	uint32_t dim0 = (uint32_t) p.dims[0];
+	uint32_t dim1 = (uint32_t) p.dims[1];
+	bool full = o0 + VM_TS <= dim0 && o1 + VM_TS <= dim1;
+
+	// ---- stage ----
+	for (int k = 0; k < p.ninputs; ++k)
+	{
+		const VmInput& in = p.in[k];
+		if (VM_IN_TILE != in.mode)
+		{
+			continue;
+		}
+		const T* data = static_cast<const T*>(in.data);
+		int32_t s0 = (int32_t) in.stride[0];
+		int32_t origin = (int32_t) in.offset + rest_offset32(p, in.stride, brest) +
+			(int32_t) o0 * s0 + (int32_t) o1 * (int32_t) in.stride[1];
+		T* tile = tiles + in.vec_ok * VM_TS * VM_TS;
+		if (ALIGNED)
+		{
+			// chunk ci = t + 256 j: row r0 = t / 16 + 16 j, 16-byte column t % 16
+			int r0 = threadIdx.x >> 4;
+			int pc = threadIdx.x & 15;
+			const T* src = data + origin + r0 * s0 + pc * 4;
+			T* dst = tile + r0 * VM_TS + ((pc ^ ((r0 >> 2) & 7)) << 2);
+			if (full)
+			{
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+				{
+					// rows 16 j further: (r0 >> 2) & 7 moves by 4 j
+					cp_async16(tile + (r0 + 16 * j) * VM_TS +
+						((pc ^ (((r0 >> 2) + 4 * j) & 7)) << 2),
+						src + 16 * j * s0, 16);
+				}
+			}
+			else
+			{
+				int left = (int) dim1 - (int) (o1 + pc * 4);
+				int row_bytes = left > 0 ? (left < 4 ? left * 4 : 16) : 0;
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+				{
+					int bytes = (o0 + r0 + 16 * j < dim0) ? row_bytes : 0;
+					cp_async16(tile + (r0 + 16 * j) * VM_TS +
+						((pc ^ (((r0 >> 2) + 4 * j) & 7)) << 2),
+						bytes > 0 ? src + 16 * j * s0 : data, bytes);
+				}
+			}
+			(void) dst;
+		}
+		else
+		{
+			T v[16];
+#pragma unroll
+			for (int j = 0; j < 16; ++j)
+			{
+				int e = threadIdx.x + VM_THREADS * j;
+				int lp = e & 63;
+				int r0 = e >> 6;
+				v[j] = T();
+				if (o1 + lp < dim1 && o0 + r0 < dim0)
+				{
+					v[j] = __ldcs(data + origin + r0 * s0 + lp);
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < 16; ++j)
+			{
+				int e = threadIdx.x + VM_THREADS * j;
+				int lp = e & 63;
+				int r0 = e >> 6;
+				tile[r0 * VM_TS + (((lp >> 2) ^ ((r0 >> 2) & 7)) << 2) + (lp & 3)] = v[j];
+			}
+		}
+	}
+	if (ALIGNED)
+	{
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+	}
+	__syncthreads();
+
+	Tile4Loader<T> loader = {p, tiles,
+		o0 + 4 * (threadIdx.x & 7),
+		o1 + 8 * (threadIdx.x >> 5) + ((threadIdx.x >> 3) & 3),
+		dim0, dim1, brest, full};
+	T acc[G::V];
+	vm_exec<T>(acc, p, loader, spill);
+	int32_t os1 = (int32_t) p.out_stride[1];
+	T* out = static_cast<T*>(p.out) + rest_offset32(p, p.out_stride, brest) +
+		(int32_t) loader.c0 + (int32_t) loader.c1 * os1;
+	if (full && p.out_vec_ok)
+	{
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			uint4 tmp;
+			T* t = reinterpret_cast<T*>(&tmp);
+#pragma unroll
+			for (int e = 0; e < 4; ++e)
+			{
+				t[e] = acc[u * 4 + e];
+			}
+			__stcs(reinterpret_cast<uint4*>(out + 32 * (u & 1) + 4 * (u >> 1) * os1), tmp);
+		}
+		return;
+	}
+#pragma unroll
+	for (int u = 0; u < 4; ++u)
+	{
+		int ok = loader.valid(u);
+		if (ok > 0)
+		{
+			store_chunk<T,4>(out + 32 * (u & 1) + 4 * (u >> 1) * os1,
+				acc + u * 4, p.out_vec_ok, ok);
+		}
+	}
+}
+
 static bool aligned16 (const void* ptr, int64_t elem_offset, size_t esize)
 {
 	return 0 == (((uintptr_t) ptr + (uintptr_t) (elem_offset * (int64_t) esize)) & 15u);
@@ -544,9 +859,9 @@ int vm_prepare (VmParams& p, int dtype, const uint64_t outshape[LLO_RANK],
 /// number of staged inputs, 0 when the flat launch should be used.
 static int plan_tiles (VmParams& p, size_t esize, int chunk, int tile0, int tilep)
 {
-	if (p.ndims < 2 || p.n >= (1ull << 31))
+	if (p.ndims < 2 || 0 == p.idx32)
 	{
-		return 0;
+		return 0; // the tile kernels address with 32-bit offsets
 	}
 	int pdim = -1;
 	for (int k = 0; k < p.ninputs && pdim < 0; ++k)
@@ -634,7 +949,68 @@ static int plan_tiles (VmParams& p, size_t esize, int chunk, int tile0, int tile
 	p.rows_aligned = 1; // tile chunks never leave their row
 	p.tiles0 = (uint32_t) ((p.dims[0] + tile0 - 1) / tile0);
 	p.tilesp = (uint32_t) ((p.dims[1] + tilep - 1) / tilep);
+	p.nstaged = nstaged;
+	p.mirror = (tile0 == tilep && p.tiles0 == p.tilesp && p.tiles0 > 1) ? 1 : 0;
+	bool aligned = true;
+	for (int k = 0; k < p.ninputs; ++k)
+	{
+		const VmInput& in = p.in[k];
+		if (VM_IN_TILE != in.mode)
+		{
+			continue;
+		}
+		aligned = aligned && aligned16(in.data, in.offset, esize);
+		for (int d = 0; d < p.ndims; ++d)
+		{
+			if (1 != d)
+			{
+				aligned = aligned && (0 == in.stride[d] % lanes16);
+			}
+		}
+	}
+	p.tile_aligned = aligned ? 1 : 0;
 	return nstaged;
+}
+
+/// Launch the tile kernel of T: the cp.async / swizzled kernel for 4-byte
+/// types, the padded-tile kernel for the others
+template <typename T>
+static int launch_tile (llo_cuda_ctx* ctx, const VmParams& p, int nstaged,
+	size_t spill, unsigned blocks)
+{
+	using G = VmGeom<T>;
+	if constexpr (4 == sizeof(T))
+	{
+		size_t smem = (size_t) nstaged * VM_TS * VM_TS * sizeof(T) + spill;
+		if (smem > 48 * 1024)
+		{
+			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_tile4_kernel<T,true>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_tile4_kernel<T,false>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+		}
+		if (p.tile_aligned)
+		{
+			vm_tile4_kernel<T,true><<<blocks, VM_THREADS, smem, ctx->stream>>>(p);
+		}
+		else
+		{
+			vm_tile4_kernel<T,false><<<blocks, VM_THREADS, smem, ctx->stream>>>(p);
+		}
+		return launched(ctx, "vm_tile4_kernel");
+	}
+	else
+	{
+		size_t smem = (size_t) VM_MAX_TILE_INPUTS * G::TILEP * G::PITCH *
+			sizeof(T) + spill;
+		if (smem > 48 * 1024)
+		{
+			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_tile_kernel<T>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+		}
+		vm_tile_kernel<T><<<blocks, VM_THREADS, smem, ctx->stream>>>(p);
+		return launched(ctx, "vm_tile_kernel");
+	}
 }
 
 int vm_launch (llo_cuda_ctx* ctx, int dtype, void* out,
@@ -664,16 +1040,7 @@ int vm_launch (llo_cuda_ctx* ctx, int dtype, void* out,
 			{
 				return fail(LLO_ERR_FATAL, "elementwise launch too large");
 			}
-			size_t smem = (size_t) VM_MAX_TILE_INPUTS * G::TILEP * G::PITCH *
-				sizeof(T) + spill;
-			if (smem > 48 * 1024)
-			{
-				LLO_CUDA_TRY(cudaFuncSetAttribute(vm_tile_kernel<T>,
-					cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-			}
-			vm_tile_kernel<T><<<(unsigned) blocks, VM_THREADS, smem,
-				ctx->stream>>>(p);
-			return launched(ctx, "vm_tile_kernel");
+			return launch_tile<T>(ctx, p, nstaged, spill, (unsigned) blocks);
 		}
 		uint64_t span = (uint64_t) VM_THREADS * G::V;
 		uint64_t blocks = (p.n + span - 1) / span;

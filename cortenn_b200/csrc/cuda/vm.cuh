@@ -148,6 +148,9 @@ struct VmParams
 	// tile launch only
 	uint32_t tiles0;
 	uint32_t tilesp;
+	int32_t nstaged;        // inputs staged through shared-memory tiles
+	int32_t tile_aligned;   // every staged row start is 16-byte aligned
+	int32_t mirror;         // square tile grid: tile (i,j) runs next to (j,i)
 	uint64_t dims[LLO_RANK];
 	int64_t out_stride[LLO_RANK]; // dense strides of the collapsed dims
 	FastDiv div[LLO_RANK];
@@ -414,6 +417,11 @@ __device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
 		int sel = p.code[pc].sel;
 		int arg = p.code[pc].arg;
 		int src = arg >> 4;
+		if (VM_S_SET == sel && VM_SRC_IN == src)
+		{
+			loader.load(acc, arg & 15); // straight into the accumulator
+			continue;
+		}
 		T x[V];
 		if (VM_SRC_IN == src)
 		{
