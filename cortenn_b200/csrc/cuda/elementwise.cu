@@ -337,26 +337,19 @@ struct Tile4Loader
 	}
 };
 
-template <typename T, bool ALIGNED>
-__global__ void __launch_bounds__(VM_THREADS, 4)
-vm_tile4_kernel (const __grid_constant__ VmParams p)
+/// Tile number -> origin of the tile (o0, o1) and index over the other dims
+__device__ __forceinline__ void tile_origin (const VmParams& p, uint32_t tile,
+	uint32_t& o0, uint32_t& o1, uint32_t& brest)
 {
-	static_assert(4 == sizeof(T), "4-byte element types only");
-	using G = VmGeom<T>;
-	extern __shared__ __align__(16) unsigned char vm_smem[];
-	T* tiles = reinterpret_cast<T*>(vm_smem);
-	T* spill = tiles + p.nstaged * VM_TS * VM_TS;
-
-	// block -> (tile along dim 0, tile along dim 1, every other dim)
 	uint32_t per = p.tiles0 * p.tilesp;
-	uint32_t brest = blockIdx.x / per;
-	uint32_t b = blockIdx.x - brest * per;
+	brest = tile / per;
+	uint32_t b = tile - brest * per;
 	uint32_t t0, tp;
 	if (p.mirror)
 	{
-		// tiles (i,j) and (j,i) get neighbouring block numbers, so an input
-		// that is read both straight and transposed (x and permute(x)) comes
-		// from DRAM once and from L2 the second time
+		// tiles (i,j) and (j,i) get neighbouring numbers, so an input that
+		// is read both straight and transposed (x and permute(x)) comes from
+		// DRAM once and from L2 the second time
 		uint32_t side = p.tiles0;
 		uint32_t off_diag = side * (side - 1);
 		if (b < off_diag)
@@ -379,13 +372,18 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 		t0 = b % p.tiles0;
 		tp = b / p.tiles0;
 	}
-	uint32_t o0 = t0 * VM_TS;
-	uint32_t o1 = tp * VM_TS;
+	o0 = t0 * VM_TS;
+	o1 = tp * VM_TS;
+}
+
+/// Stage every transposed input's tile at (o0, o1) into `tiles`
+template <typename T, bool ALIGNED>
+__device__ __forceinline__ void stage_tiles (const VmParams& p, T* tiles,
+	uint32_t o0, uint32_t o1, uint32_t brest)
+{
 	uint32_t dim0 = (uint32_t) p.dims[0];
 	uint32_t dim1 = (uint32_t) p.dims[1];
 	bool full = o0 + VM_TS <= dim0 && o1 + VM_TS <= dim1;
-
-	// ---- stage ----
 	for (int k = 0; k < p.ninputs; ++k)
 	{
 		const VmInput& in = p.in[k];
@@ -400,17 +398,16 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 		T* tile = tiles + in.vec_ok * VM_TS * VM_TS;
 		if (ALIGNED)
 		{
-			// chunk ci = t + 256 j: row r0 = t / 16 + 16 j, 16-byte column t % 16
+			// chunk ci = t + 256 j: row r0 = t / 16 + 16 j, 16-byte column t % 16;
+			// 16 rows further the swizzle key (r0 >> 2) & 7 moves by 4
 			int r0 = threadIdx.x >> 4;
 			int pc = threadIdx.x & 15;
 			const T* src = data + origin + r0 * s0 + pc * 4;
-			T* dst = tile + r0 * VM_TS + ((pc ^ ((r0 >> 2) & 7)) << 2);
 			if (full)
 			{
 #pragma unroll
 				for (int j = 0; j < 4; ++j)
 				{
-					// rows 16 j further: (r0 >> 2) & 7 moves by 4 j
 					cp_async16(tile + (r0 + 16 * j) * VM_TS +
 						((pc ^ (((r0 >> 2) + 4 * j) & 7)) << 2),
 						src + 16 * j * s0, 16);
@@ -429,7 +426,6 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 						bytes > 0 ? src + 16 * j * s0 : data, bytes);
 				}
 			}
-			(void) dst;
 		}
 		else
 		{
@@ -456,13 +452,17 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 			}
 		}
 	}
-	if (ALIGNED)
-	{
-		asm volatile("cp.async.commit_group;" ::: "memory");
-		asm volatile("cp.async.wait_group 0;" ::: "memory");
-	}
-	__syncthreads();
+}
 
+/// Run the program for the output tile at (o0, o1) and store it
+template <typename T>
+__device__ __forceinline__ void run_tile (const VmParams& p, const T* tiles,
+	T* spill, uint32_t o0, uint32_t o1, uint32_t brest)
+{
+	using G = VmGeom<T>;
+	uint32_t dim0 = (uint32_t) p.dims[0];
+	uint32_t dim1 = (uint32_t) p.dims[1];
+	bool full = o0 + VM_TS <= dim0 && o1 + VM_TS <= dim1;
 	Tile4Loader<T> loader = {p, tiles,
 		o0 + 4 * (threadIdx.x & 7),
 		o1 + 8 * (threadIdx.x >> 5) + ((threadIdx.x >> 3) & 3),
@@ -496,6 +496,62 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 		{
 			store_chunk<T,4>(out + 32 * (u & 1) + 4 * (u >> 1) * os1,
 				acc + u * 4, p.out_vec_ok, ok);
+		}
+	}
+}
+
+/// Persistent: CTA c handles tiles c, c + grid, ...  With ALIGNED staging the
+/// cp.async copies of the next tile fly while the current one is computed
+/// (two tile buffers); the scalar fallback stages and computes in turn.
+template <typename T, bool ALIGNED>
+__global__ void __launch_bounds__(VM_THREADS, 3)
+vm_tile4_kernel (const __grid_constant__ VmParams p)
+{
+	static_assert(4 == sizeof(T), "4-byte element types only");
+	extern __shared__ __align__(16) unsigned char vm_smem[];
+	T* tiles = reinterpret_cast<T*>(vm_smem);
+	const int buf_elems = p.nstaged * VM_TS * VM_TS;
+	T* spill = tiles + (ALIGNED ? 2 : 1) * buf_elems;
+	uint32_t o0, o1, brest;
+	if (ALIGNED)
+	{
+		uint32_t tile = blockIdx.x;
+		tile_origin(p, tile, o0, o1, brest);
+		stage_tiles<T,true>(p, tiles, o0, o1, brest);
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		int buf = 0;
+		while (tile < p.total_tiles)
+		{
+			uint32_t next = tile + gridDim.x;
+			if (next < p.total_tiles)
+			{
+				uint32_t n0, n1, nrest;
+				tile_origin(p, next, n0, n1, nrest);
+				stage_tiles<T,true>(p, tiles + (buf ^ 1) * buf_elems, n0, n1, nrest);
+				asm volatile("cp.async.commit_group;" ::: "memory");
+				asm volatile("cp.async.wait_group 1;" ::: "memory");
+			}
+			else
+			{
+				asm volatile("cp.async.wait_group 0;" ::: "memory");
+			}
+			__syncthreads();
+			tile_origin(p, tile, o0, o1, brest);
+			run_tile<T>(p, tiles + buf * buf_elems, spill, o0, o1, brest);
+			__syncthreads(); // everyone is done with this buffer
+			buf ^= 1;
+			tile = next;
+		}
+	}
+	else
+	{
+		for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+		{
+			tile_origin(p, tile, o0, o1, brest);
+			stage_tiles<T,false>(p, tiles, o0, o1, brest);
+			__syncthreads();
+			run_tile<T>(p, tiles, spill, o0, o1, brest);
+			__syncthreads();
 		}
 	}
 }
@@ -975,19 +1031,28 @@ static int plan_tiles (VmParams& p, size_t esize, int chunk, int tile0, int tile
 /// Launch the tile kernel of T: the cp.async / swizzled kernel for 4-byte
 /// types, the padded-tile kernel for the others
 template <typename T>
-static int launch_tile (llo_cuda_ctx* ctx, const VmParams& p, int nstaged,
+static int launch_tile (llo_cuda_ctx* ctx, VmParams& p, int nstaged,
 	size_t spill, unsigned blocks)
 {
+	p.total_tiles = blocks;
 	using G = VmGeom<T>;
 	if constexpr (4 == sizeof(T))
 	{
-		size_t smem = (size_t) nstaged * VM_TS * VM_TS * sizeof(T) + spill;
+		size_t smem = (size_t) (p.tile_aligned ? 2 : 1) * nstaged * VM_TS * VM_TS *
+			sizeof(T) + spill;
+		unsigned cap = (unsigned) ctx->sm_count * 3;
+		cap += cap & 1;
+		if (blocks > cap)
+		{
+			// persistent: an even CTA count keeps mirror pairs side by side
+			blocks = cap;
+		}
 		if (smem > 48 * 1024)
 		{
 			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_tile4_kernel<T,true>,
-				cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+				cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
 			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_tile4_kernel<T,false>,
-				cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+				cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
 		}
 		if (p.tile_aligned)
 		{

@@ -151,6 +151,7 @@ struct VmParams
 	int32_t nstaged;        // inputs staged through shared-memory tiles
 	int32_t tile_aligned;   // every staged row start is 16-byte aligned
 	int32_t mirror;         // square tile grid: tile (i,j) runs next to (j,i)
+	uint32_t total_tiles;   // tiles of the whole launch (persistent kernels)
 	uint64_t dims[LLO_RANK];
 	int64_t out_stride[LLO_RANK]; // dense strides of the collapsed dims
 	FastDiv div[LLO_RANK];
