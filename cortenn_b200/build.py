@@ -35,7 +35,7 @@ NVCC_FLAGS = [
     "-I", INCLUDE, "-I", os.path.join(CSRC, "cuda"),
 ]
 # kernels whose FMAs are written out explicitly keep contraction on
-NVCC_FMAD_OK = {"gemm.cu"}
+NVCC_FMAD_OK = {"gemm.cu"}  # (sgemm.cu / dgemm.cu spell their FMAs as fmaf / fma)
 
 CXX_FLAGS = [
     "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden",

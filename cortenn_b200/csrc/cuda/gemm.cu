@@ -114,6 +114,16 @@ extern "C" int llo_cuda_gemm (llo_cuda_ctx* ctx, int dtype,
 	{
 		return fail(LLO_ERR_FATAL, "the 3xTF32 path is defined for FLOAT only");
 	}
+	else if (LLO_DT_DOUBLE == dtype)
+	{
+		bool handled = false;
+		LLO_TRY(dgemm_launch(ctx, p, (double*) C, (const double*) A,
+			(const double*) B, handled));
+		if (handled)
+		{
+			return LLO_OK;
+		}
+	}
 	dim3 grid((unsigned) ((N + 31) / 32), (unsigned) ((M + 31) / 32));
 	LLO_DISPATCH_DTYPE(dtype, T,
 	{

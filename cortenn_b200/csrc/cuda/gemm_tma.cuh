@@ -1,0 +1,358 @@
+///
+/// gemm_tma.cuh — what the TMA-staged FMA-pipe GEMMs share (sgemm.cu fp32,
+/// dgemm.cu fp64): mbarrier / TMA device helpers, tensor-map construction,
+/// re-pitching of operands TMA cannot address, split-K with a fixed-order
+/// second pass, and the host driver that normalises a GemmParams problem.
+///
+
+#ifndef LLO_CUDA_GEMM_TMA_CUH
+#define LLO_CUDA_GEMM_TMA_CUH
+
+#include <algorithm>
+#include <utility>
+
+#include <cuda.h>
+
+#include "gemm.cuh"
+
+namespace llo_cuda
+{
+
+namespace tma
+{
+
+template <typename T>
+struct GemmArgs
+{
+	T* C;
+	int64_t c_rs;      // row stride of C in elements (columns are contiguous)
+	uint32_t M;
+	uint32_t N;
+	uint32_t K;
+	uint32_t tiles_m;
+	uint32_t tiles_n;
+	uint32_t vec_store; // C rows allow aligned vector stores
+	// split-K: CTA (tile, y) reduces k-tiles [y * kt_per_split, +kt_per_split)
+	// into the partial product C + y * split_stride
+	uint32_t kt_per_split;
+	int64_t split_stride;
+};
+
+__device__ __forceinline__ uint32_t smem_u32 (const void* p)
+{
+	return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init (uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;"
+		:: "r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx (uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+		:: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive (uint64_t* bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
+		:: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait (uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred P1;\n"
+		"LAB_WAIT:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+		"@P1 bra DONE;\n"
+		"bra LAB_WAIT;\n"
+		"DONE:\n"
+		"}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d (void* dst, const CUtensorMap* map,
+	uint64_t* bar, int c0, int c1)
+{
+	asm volatile(
+		"cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+		" [%0], [%1, {%3, %4}], [%2];"
+		:: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+		: "memory");
+}
+
+
+// ---- host side -----------------------------------------------------------------
+
+using EncodeFn = CUresult (*) (CUtensorMap*, CUtensorMapDataType, cuuint32_t,
+	void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+	const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+	CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeFn tensor_map_encoder (void)
+{
+	static EncodeFn fn = nullptr;
+	static bool tried = false;
+	if (false == tried)
+	{
+		tried = true;
+		void* sym = nullptr;
+		cudaDriverEntryPointQueryResult status;
+		if (cudaSuccess == cudaGetDriverEntryPoint("cuTensorMapEncodeTiled",
+			&sym, cudaEnableDefault, &status) &&
+			cudaDriverEntryPointSuccess == status)
+		{
+			fn = (EncodeFn) sym;
+		}
+		cudaGetLastError();
+	}
+	return fn;
+}
+
+/// 2-D tensor map: `inner` contiguous elements, `outer` rows of
+/// `outer_stride` elements; box = box_inner x box_outer
+template <typename T>
+bool make_map (CUtensorMap& map, const T* base, uint64_t inner,
+	uint64_t outer, int64_t outer_stride, uint32_t box_inner,
+	uint32_t box_outer, bool swizzle)
+{
+	EncodeFn encode = tensor_map_encoder();
+	if (nullptr == encode)
+	{
+		return false;
+	}
+	cuuint64_t dims[2] = {inner, outer};
+	cuuint64_t strides[1] = {(cuuint64_t) outer_stride * sizeof(T)};
+	cuuint32_t box[2] = {box_inner, box_outer};
+	cuuint32_t estrides[2] = {1, 1};
+	CUresult rc = encode(&map, 8 == sizeof(T) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 :
+		CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+		(void*) base, dims, strides, box, estrides,
+		CU_TENSOR_MAP_INTERLEAVE_NONE,
+		swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+		CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return CUDA_SUCCESS == rc;
+}
+
+template <typename T>
+bool operand_ok (const T* base, int64_t lead)
+{
+	return 0 == ((uintptr_t) base & 15u) && lead > 0 &&
+		0 == (lead * (int64_t) sizeof(T)) % 16 && lead < (1ll << 37);
+}
+
+/// dst[r * dst_ld + c] = src[r * src_ld + c]: re-pitch an operand whose rows
+/// TMA cannot address (pitch not a multiple of 16 bytes, e.g. the 10-wide
+/// last layer of the MLP)
+template <typename T>
+__global__ void __launch_bounds__(256)
+repitch_kernel (T* __restrict__ dst, const T* __restrict__ src,
+	uint64_t rows, uint32_t cols, int64_t src_ld, int64_t dst_ld)
+{
+	uint64_t i = (uint64_t) blockIdx.x * 256 + threadIdx.x;
+	uint64_t r = i / cols;
+	uint32_t c = (uint32_t) (i - r * cols);
+	if (r < rows)
+	{
+		dst[r * dst_ld + c] = __ldg(src + r * src_ld + c);
+	}
+}
+
+/// C[m * c_rs + n] = sum over s (ascending) of part[s][m][n]: the fixed-order
+/// second pass of split-K
+template <typename T>
+__global__ void __launch_bounds__(256)
+splitk_fold_kernel (T* __restrict__ C, int64_t c_rs,
+	const T* __restrict__ part, uint32_t M, uint32_t N, int64_t ld,
+	int64_t split_stride, uint32_t splits)
+{
+	uint64_t i = (uint64_t) blockIdx.x * 256 + threadIdx.x;
+	uint64_t m = i / N;
+	uint32_t n = (uint32_t) (i - m * N);
+	if (m >= M)
+	{
+		return;
+	}
+	const T* p = part + m * ld + n;
+	T acc = __ldcs(p);
+	for (uint32_t s = 1; s < splits; ++s)
+	{
+		acc = acc + __ldcs(p + (int64_t) s * split_stride); // no contraction possible
+	}
+	C[m * c_rs + n] = acc;
+}
+
+/// Make `base` (rows x cols, row pitch `lead`) addressable by TMA, copying it
+/// to a 16-byte pitched scratch buffer when it is not
+template <typename T>
+int make_ready (llo_cuda_ctx* ctx, Scratch& scratch, const T*& base,
+	int64_t& lead, uint64_t rows, uint64_t cols)
+{
+	if (operand_ok(base, lead))
+	{
+		return LLO_OK;
+	}
+	if (lead < (int64_t) cols && rows > 1)
+	{
+		return fail(LLO_ERR_FATAL, "gemm operand rows overlap");
+	}
+	int64_t unit = (int64_t) (16 / sizeof(T));
+	int64_t ld = (int64_t) ((cols + unit - 1) / unit * unit);
+	void* copy = nullptr;
+	LLO_TRY(scratch.get(&copy, (size_t) rows * ld * sizeof(T)));
+	uint64_t total = rows * cols;
+	repitch_kernel<T><<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(
+		(T*) copy, base, rows, (uint32_t) cols, lead, ld);
+	LLO_TRY(launched(ctx, "repitch_kernel"));
+	base = (const T*) copy;
+	lead = ld;
+	return LLO_OK;
+}
+
+/// Normalise the problem (row-major C, contiguous operand directions), build
+/// the tensor maps, choose split-K, and call
+///   launch(ak, bk, map_a, map_b, args, splits) -> status
+/// `vec_a` / `vec_b` give the C store vector width (elements) per B layout.
+template <typename T, int BM, int BN, int BK, typename Launch>
+int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
+	const T* B, bool& handled, int vec_nc, int vec_kc, Launch launch)
+{
+	handled = false;
+	GemmParams p = p0;
+	// C must have contiguous columns; a column-major C is the row-major C^T
+	// of the transposed product B^T A^T
+	if (1 != p.c_cs && p.N > 1)
+	{
+		if (1 != p.c_rs && p.M > 1)
+		{
+			return LLO_OK;
+		}
+		std::swap(p.M, p.N);
+		std::swap(A, B);
+		int64_t a_rs = p.b_cs, a_cs = p.b_rs, b_rs = p.a_cs, b_cs = p.a_rs;
+		p.a_rs = a_rs; p.a_cs = a_cs; p.b_rs = b_rs; p.b_cs = b_cs;
+		std::swap(p.c_rs, p.c_cs);
+	}
+	if (p.M * p.N * p.K < 32768 ||
+		p.M >= (1ull << 31) || p.N >= (1ull << 31) || p.K >= (1ull << 31))
+	{
+		return LLO_OK; // tiny / huge problems take the generic kernel
+	}
+	if (nullptr == tensor_map_encoder())
+	{
+		return LLO_OK;
+	}
+	// a 1-long dimension has no meaningful stride: pick the contiguous form
+	if (1 == p.K) { p.a_cs = 1; p.b_rs = 1; }
+	if (1 == p.M) { p.a_rs = (1 == p.a_cs) ? (int64_t) p.K : 1; }
+	if (1 == p.N) { p.b_cs = (1 == p.b_rs) ? (int64_t) p.K : 1; p.c_cs = 1; }
+	bool ak = (1 == p.a_cs);
+	bool bk = (1 == p.b_rs);
+	if ((false == ak && 1 != p.a_rs) || (false == bk && 1 != p.b_cs))
+	{
+		return LLO_OK;
+	}
+	int64_t lead_a = ak ? p.a_rs : p.a_cs;
+	int64_t lead_b = bk ? p.b_cs : p.b_rs;
+	if (lead_a <= 0 || lead_b <= 0)
+	{
+		return LLO_OK; // broadcast or mirrored operands
+	}
+	Scratch scratch(ctx);
+	LLO_TRY(make_ready(ctx, scratch, A, lead_a, ak ? p.M : p.K, ak ? p.K : p.M));
+	LLO_TRY(make_ready(ctx, scratch, B, lead_b, bk ? p.N : p.K, bk ? p.K : p.N));
+	CUtensorMap ma, mb;
+	bool ok = ak ?
+		make_map(ma, A, p.K, p.M, lead_a, BK, BM, true) :
+		make_map(ma, A, p.M, p.K, lead_a, BM, BK, false);
+	ok = ok && (bk ?
+		make_map(mb, B, p.K, p.N, lead_b, BK, BN, true) :
+		make_map(mb, B, p.N, p.K, lead_b, BN, BK, false));
+	if (false == ok)
+	{
+		return LLO_OK;
+	}
+	GemmArgs<T> args;
+	args.M = (uint32_t) p.M;
+	args.N = (uint32_t) p.N;
+	args.K = (uint32_t) p.K;
+	args.tiles_m = (uint32_t) ((p.M + BM - 1) / BM);
+	args.tiles_n = (uint32_t) ((p.N + BN - 1) / BN);
+	uint64_t tiles = (uint64_t) args.tiles_m * args.tiles_n;
+	if (tiles >= 0x7fffffffull)
+	{
+		return LLO_OK;
+	}
+	// split-K: when the output has fewer tiles than the chip has SMs, the
+	// k-tiles of every output tile are spread over `splits` CTAs and the
+	// partial products are summed in split order by a second pass
+	uint32_t ktiles = (uint32_t) ((p.K + BK - 1) / BK);
+	uint32_t splits = 1;
+	if (tiles * 2 <= (uint64_t) ctx->sm_count && ktiles >= 16)
+	{
+		// pick the split count whose grid fills whole waves of SMs best
+		// (ties: fewer splits), between ~1 and ~4 waves
+		uint64_t sms = (uint64_t) ctx->sm_count;
+		uint64_t most = std::min<uint64_t>(ktiles / 8, 64);
+		uint64_t lo = std::max<uint64_t>(2, sms / tiles);
+		uint64_t hi = std::min<uint64_t>(most, (4 * sms + tiles - 1) / tiles);
+		double best = 0;
+		for (uint64_t cand = lo; cand <= hi; ++cand)
+		{
+			uint64_t ctas = tiles * cand;
+			uint64_t waves = (ctas + sms - 1) / sms;
+			double fill = (double) ctas / (double) (waves * sms);
+			if (fill > best + 0.02)
+			{
+				best = fill;
+				splits = (uint32_t) cand;
+			}
+		}
+	}
+	args.kt_per_split = (ktiles + splits - 1) / splits;
+	splits = (ktiles + args.kt_per_split - 1) / args.kt_per_split;
+	int64_t need = bk ? vec_kc : vec_nc;
+	T* part = nullptr;
+	int64_t part_ld = 0;
+	if (splits > 1)
+	{
+		int64_t unit = (int64_t) (16 / sizeof(T));
+		part_ld = (int64_t) ((p.N + unit - 1) / unit * unit);
+		void* ws = nullptr;
+		LLO_TRY(scratch.get(&ws, (size_t) splits * p.M * part_ld * sizeof(T)));
+		part = (T*) ws;
+		args.C = part;
+		args.c_rs = part_ld;
+		args.split_stride = (int64_t) p.M * part_ld;
+		args.vec_store = 1;
+	}
+	else
+	{
+		args.C = C;
+		args.c_rs = p.c_rs;
+		args.split_stride = 0;
+		args.vec_store = (0 == ((uintptr_t) C & (uintptr_t) (need * sizeof(T) - 1)) &&
+			0 == p.c_rs % need) ? 1 : 0;
+	}
+	handled = true;
+	LLO_TRY(launch(ak, bk, ma, mb, args, splits));
+	if (splits > 1)
+	{
+		uint64_t total = p.M * p.N;
+		splitk_fold_kernel<T><<<(unsigned) ((total + 255) / 256), 256, 0,
+			ctx->stream>>>(C, p.c_rs, part, (uint32_t) p.M, (uint32_t) p.N,
+			part_ld, args.split_stride, splits);
+		LLO_TRY(launched(ctx, "splitk_fold_kernel"));
+	}
+	return LLO_OK;
+}
+
+}
+
+}
+
+#endif // LLO_CUDA_GEMM_TMA_CUH

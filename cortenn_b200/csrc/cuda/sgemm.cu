@@ -27,12 +27,7 @@
 ///   Out-of-range parts of edge tiles are zero-filled by TMA and add 0.
 ///
 
-#include <algorithm>
-#include <utility>
-
-#include <cuda.h>
-
-#include "gemm.cuh"
+#include "gemm_tma.cuh"
 
 namespace llo_cuda
 {
@@ -58,67 +53,8 @@ constexpr size_t SMEM_BYTES = 1024 /* alignment slack */ +
 // slack keep the refilling warp from ever waiting on a slower warp
 constexpr uint32_t LEAD = STAGES - 2;
 
-struct SgemmArgs
-{
-	float* C;
-	int64_t c_rs;      // row stride of C in elements (columns are contiguous)
-	uint32_t M;
-	uint32_t N;
-	uint32_t K;
-	uint32_t tiles_m;
-	uint32_t tiles_n;
-	uint32_t vec_store; // C rows allow aligned 128-bit stores
-	// split-K: CTA (tile, y) reduces k-tiles [y * kt_per_split, +kt_per_split)
-	// into the partial product C + y * split_stride
-	uint32_t kt_per_split;
-	int64_t split_stride;
-};
-
-__device__ __forceinline__ uint32_t smem_u32 (const void* p)
-{
-	return (uint32_t) __cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void mbar_init (uint64_t* bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;"
-		:: "r"(smem_u32(bar)), "r"(count));
-}
-
-__device__ __forceinline__ void mbar_expect_tx (uint64_t* bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-		:: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive (uint64_t* bar)
-{
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
-		:: "r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait (uint64_t* bar, uint32_t parity)
-{
-	asm volatile(
-		"{\n"
-		".reg .pred P1;\n"
-		"LAB_WAIT:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-		"@P1 bra DONE;\n"
-		"bra LAB_WAIT;\n"
-		"DONE:\n"
-		"}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-__device__ __forceinline__ void tma_load_2d (void* dst, const CUtensorMap* map,
-	uint64_t* bar, int c0, int c1)
-{
-	asm volatile(
-		"cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-		" [%0], [%1, {%3, %4}], [%2];"
-		:: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-		: "memory");
-}
+using SgemmArgs = tma::GemmArgs<float>;
+using namespace tma;
 
 __device__ __forceinline__ float comp (const float4& v, int k)
 {
@@ -464,100 +400,6 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 
 // ---- host side -----------------------------------------------------------------
 
-using EncodeFn = CUresult (*) (CUtensorMap*, CUtensorMapDataType, cuuint32_t,
-	void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-	const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-	CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeFn tensor_map_encoder (void)
-{
-	static EncodeFn fn = nullptr;
-	static bool tried = false;
-	if (false == tried)
-	{
-		tried = true;
-		void* sym = nullptr;
-		cudaDriverEntryPointQueryResult status;
-		if (cudaSuccess == cudaGetDriverEntryPoint("cuTensorMapEncodeTiled",
-			&sym, cudaEnableDefault, &status) &&
-			cudaDriverEntryPointSuccess == status)
-		{
-			fn = (EncodeFn) sym;
-		}
-		cudaGetLastError();
-	}
-	return fn;
-}
-
-/// 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows of
-/// `outer_stride` elements; box = box_inner x box_outer
-bool make_map (CUtensorMap& map, const float* base, uint64_t inner,
-	uint64_t outer, int64_t outer_stride, uint32_t box_inner,
-	uint32_t box_outer, bool swizzle)
-{
-	EncodeFn encode = tensor_map_encoder();
-	if (nullptr == encode)
-	{
-		return false;
-	}
-	cuuint64_t dims[2] = {inner, outer};
-	cuuint64_t strides[1] = {(cuuint64_t) outer_stride * sizeof(float)};
-	cuuint32_t box[2] = {box_inner, box_outer};
-	cuuint32_t estrides[2] = {1, 1};
-	CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-		(void*) base, dims, strides, box, estrides,
-		CU_TENSOR_MAP_INTERLEAVE_NONE,
-		swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-		CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-		CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-	return CUDA_SUCCESS == rc;
-}
-
-bool tma_operand_ok (const float* base, int64_t lead)
-{
-	return 0 == ((uintptr_t) base & 15u) && lead > 0 && 0 == lead % 4 &&
-		lead < (1ll << 38);
-}
-
-/// dst[r * dst_ld + c] = src[r * src_ld + c]: re-pitch an operand whose rows
-/// TMA cannot address (pitch not a multiple of 16 bytes, e.g. the 10-wide
-/// last layer of the MLP)
-__global__ void __launch_bounds__(256)
-repitch_kernel (float* __restrict__ dst, const float* __restrict__ src,
-	uint64_t rows, uint32_t cols, int64_t src_ld, int64_t dst_ld)
-{
-	uint64_t i = (uint64_t) blockIdx.x * 256 + threadIdx.x;
-	uint64_t r = i / cols;
-	uint32_t c = (uint32_t) (i - r * cols);
-	if (r < rows)
-	{
-		dst[r * dst_ld + c] = __ldg(src + r * src_ld + c);
-	}
-}
-
-/// C[m * c_rs + n] = sum over s (ascending) of part[s][m][n]: the fixed-order
-/// second pass of split-K
-__global__ void __launch_bounds__(256)
-splitk_fold_kernel (float* __restrict__ C, int64_t c_rs,
-	const float* __restrict__ part, uint32_t M, uint32_t N, int64_t ld,
-	int64_t split_stride, uint32_t splits)
-{
-	uint64_t i = (uint64_t) blockIdx.x * 256 + threadIdx.x;
-	uint64_t m = i / N;
-	uint32_t n = (uint32_t) (i - m * N);
-	if (m >= M)
-	{
-		return;
-	}
-	const float* p = part + m * ld + n;
-	float acc = __ldcs(p);
-	for (uint32_t s = 1; s < splits; ++s)
-	{
-		acc = __fadd_rn(acc, __ldcs(p + (int64_t) s * split_stride));
-	}
-	C[m * c_rs + n] = acc;
-}
-
 template <bool AK, bool BKC>
 int launch_variant (llo_cuda_ctx* ctx, const CUtensorMap& ma,
 	const CUtensorMap& mb, const SgemmArgs& args, uint32_t splits)
@@ -570,34 +412,9 @@ int launch_variant (llo_cuda_ctx* ctx, const CUtensorMap& ma,
 	return launched(ctx, "sgemm_tma_kernel");
 }
 
-/// Make `base` (rows x cols, row pitch `lead`) addressable by TMA, copying it
-/// to a 16-byte pitched scratch buffer when it is not
-int tma_ready (llo_cuda_ctx* ctx, Scratch& scratch, const float*& base,
-	int64_t& lead, uint64_t rows, uint64_t cols)
-{
-	if (tma_operand_ok(base, lead))
-	{
-		return LLO_OK;
-	}
-	if (lead < (int64_t) cols && rows > 1)
-	{
-		return fail(LLO_ERR_FATAL, "gemm operand rows overlap");
-	}
-	int64_t ld = (int64_t) ((cols + 3) / 4 * 4);
-	void* copy = nullptr;
-	LLO_TRY(scratch.get(&copy, (size_t) rows * ld * sizeof(float)));
-	uint64_t total = rows * cols;
-	repitch_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(
-		(float*) copy, base, rows, (uint32_t) cols, lead, ld);
-	LLO_TRY(launched(ctx, "repitch_kernel"));
-	base = (const float*) copy;
-	lead = ld;
-	return LLO_OK;
 }
 
-}
-
-int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p0, float* C,
+int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p, float* C,
 	const float* A, const float* B, int precision, bool& handled)
 {
 	handled = false;
@@ -605,143 +422,18 @@ int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p0, float* C,
 	{
 		return LLO_OK; // 3xTF32 not wired yet: the exact path is always valid
 	}
-	GemmParams p = p0;
-	// C must have contiguous columns; a column-major C is the row-major C^T
-	// of the transposed product B^T A^T
-	if (1 != p.c_cs && p.N > 1)
-	{
-		if (1 != p.c_rs && p.M > 1)
+	return tma::drive<float,BM,BN,BK>(ctx, p, C, A, B, handled, 4, 2,
+		[ctx] (bool ak, bool bk, const CUtensorMap& ma, const CUtensorMap& mb,
+			const SgemmArgs& args, uint32_t splits) -> int
 		{
-			return LLO_OK;
-		}
-		std::swap(p.M, p.N);
-		std::swap(A, B);
-		int64_t a_rs = p.b_cs, a_cs = p.b_rs, b_rs = p.a_cs, b_cs = p.a_rs;
-		p.a_rs = a_rs; p.a_cs = a_cs; p.b_rs = b_rs; p.b_cs = b_cs;
-		std::swap(p.c_rs, p.c_cs);
-	}
-	if (p.M * p.N * p.K < 32768 ||
-		p.M >= (1ull << 31) || p.N >= (1ull << 31) || p.K >= (1ull << 31))
-	{
-		return LLO_OK; // tiny / huge problems take the generic kernel
-	}
-	if (nullptr == tensor_map_encoder())
-	{
-		return LLO_OK;
-	}
-	// a 1-long dimension has no meaningful stride: pick the contiguous form
-	if (1 == p.K) { p.a_cs = 1; p.b_rs = 1; }
-	if (1 == p.M) { p.a_rs = (1 == p.a_cs) ? (int64_t) p.K : 1; }
-	if (1 == p.N) { p.b_cs = (1 == p.b_rs) ? (int64_t) p.K : 1; p.c_cs = 1; }
-	bool ak = (1 == p.a_cs);
-	bool bk = (1 == p.b_rs);
-	if ((false == ak && 1 != p.a_rs) || (false == bk && 1 != p.b_cs))
-	{
-		return LLO_OK;
-	}
-	int64_t lead_a = ak ? p.a_rs : p.a_cs;
-	int64_t lead_b = bk ? p.b_cs : p.b_rs;
-	if (lead_a <= 0 || lead_b <= 0)
-	{
-		return LLO_OK; // broadcast or mirrored operands
-	}
-	Scratch scratch(ctx);
-	LLO_TRY(tma_ready(ctx, scratch, A, lead_a, ak ? p.M : p.K, ak ? p.K : p.M));
-	LLO_TRY(tma_ready(ctx, scratch, B, lead_b, bk ? p.N : p.K, bk ? p.K : p.N));
-	CUtensorMap ma, mb;
-	bool ok = ak ?
-		make_map(ma, A, p.K, p.M, lead_a, BK, BM, true) :
-		make_map(ma, A, p.M, p.K, lead_a, BM, BK, false);
-	ok = ok && (bk ?
-		make_map(mb, B, p.K, p.N, lead_b, BK, BN, true) :
-		make_map(mb, B, p.N, p.K, lead_b, BN, BK, false));
-	if (false == ok)
-	{
-		return LLO_OK;
-	}
-	SgemmArgs args;
-	args.M = (uint32_t) p.M;
-	args.N = (uint32_t) p.N;
-	args.K = (uint32_t) p.K;
-	args.tiles_m = (uint32_t) ((p.M + BM - 1) / BM);
-	args.tiles_n = (uint32_t) ((p.N + BN - 1) / BN);
-	uint64_t tiles = (uint64_t) args.tiles_m * args.tiles_n;
-	if (tiles >= 0x7fffffffull)
-	{
-		return LLO_OK;
-	}
-	// split-K: when the output has fewer tiles than the chip has SMs, the
-	// k-tiles of every output tile are spread over `splits` CTAs and the
-	// partial products are summed in split order by a second pass
-	uint32_t ktiles = (uint32_t) ((p.K + BK - 1) / BK);
-	uint32_t splits = 1;
-	if (tiles * 2 <= (uint64_t) ctx->sm_count && ktiles >= 16)
-	{
-		// pick the split count whose grid fills whole waves of SMs best
-		// (ties: fewer splits), between ~1 and ~4 waves
-		uint64_t sms = (uint64_t) ctx->sm_count;
-		uint64_t most = std::min<uint64_t>(ktiles / 8, 64);
-		uint64_t lo = std::max<uint64_t>(2, sms / tiles);
-		uint64_t hi = std::min<uint64_t>(most, (4 * sms + tiles - 1) / tiles);
-		double best = 0;
-		for (uint64_t cand = lo; cand <= hi; ++cand)
-		{
-			uint64_t ctas = tiles * cand;
-			uint64_t waves = (ctas + sms - 1) / sms;
-			double fill = (double) ctas / (double) (waves * sms);
-			if (fill > best + 0.02)
+			if (ak)
 			{
-				best = fill;
-				splits = (uint32_t) cand;
+				return bk ? launch_variant<true,true>(ctx, ma, mb, args, splits) :
+					launch_variant<true,false>(ctx, ma, mb, args, splits);
 			}
-		}
-	}
-	args.kt_per_split = (ktiles + splits - 1) / splits;
-	splits = (ktiles + args.kt_per_split - 1) / args.kt_per_split;
-	int64_t need = bk ? 2 : 4;
-	float* part = nullptr;
-	int64_t part_ld = 0;
-	if (splits > 1)
-	{
-		part_ld = (int64_t) ((p.N + 3) / 4 * 4);
-		void* ws = nullptr;
-		LLO_TRY(scratch.get(&ws, (size_t) splits * p.M * part_ld * sizeof(float)));
-		part = (float*) ws;
-		args.C = part;
-		args.c_rs = part_ld;
-		args.split_stride = (int64_t) p.M * part_ld;
-		args.vec_store = 1;
-	}
-	else
-	{
-		args.C = C;
-		args.c_rs = p.c_rs;
-		args.split_stride = 0;
-		args.vec_store = (0 == ((uintptr_t) C & (uintptr_t) (need * 4 - 1)) &&
-			0 == p.c_rs % need) ? 1 : 0;
-	}
-	handled = true;
-	int rc = LLO_OK;
-	if (ak)
-	{
-		rc = bk ? launch_variant<true,true>(ctx, ma, mb, args, splits) :
-			launch_variant<true,false>(ctx, ma, mb, args, splits);
-	}
-	else
-	{
-		rc = bk ? launch_variant<false,true>(ctx, ma, mb, args, splits) :
-			launch_variant<false,false>(ctx, ma, mb, args, splits);
-	}
-	LLO_TRY(rc);
-	if (splits > 1)
-	{
-		uint64_t total = p.M * p.N;
-		splitk_fold_kernel<<<(unsigned) ((total + 255) / 256), 256, 0,
-			ctx->stream>>>(C, p.c_rs, part, (uint32_t) p.M, (uint32_t) p.N,
-			part_ld, args.split_stride, splits);
-		LLO_TRY(launched(ctx, "splitk_fold_kernel"));
-	}
-	return LLO_OK;
+			return bk ? launch_variant<false,true>(ctx, ma, mb, args, splits) :
+				launch_variant<false,false>(ctx, ma, mb, args, splits);
+		});
 }
 
 }
