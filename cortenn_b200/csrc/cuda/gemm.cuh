@@ -26,6 +26,10 @@ struct GemmParams
 int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p, float* C,
 	const float* A, const float* B, int precision, bool& handled);
 
+/// tf32gemm.cu: opt-in 3xTF32 tensor-core path (tcgen05 + TMEM) for fp32
+int tf32x3_launch (llo_cuda_ctx* ctx, const GemmParams& p, float* C,
+	const float* A, const float* B, bool& handled);
+
 /// dgemm.cu: DFMA path for fp64, same contract
 int dgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p, double* C,
 	const double* A, const double* B, bool& handled);

@@ -418,9 +418,14 @@ int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p, float* C,
 	const float* A, const float* B, int precision, bool& handled)
 {
 	handled = false;
-	if (LLO_GEMM_EXACT != precision)
+	if (LLO_GEMM_3XTF32 == precision)
 	{
-		return LLO_OK; // 3xTF32 not wired yet: the exact path is always valid
+		LLO_TRY(tf32x3_launch(ctx, p, C, A, B, handled));
+		if (handled)
+		{
+			return LLO_OK;
+		}
+		// shapes the tensor-core kernel declines run exactly
 	}
 	return tma::drive<float,BM,BN,BK>(ctx, p, C, A, B, handled, 4, 2,
 		[ctx] (bool ak, bool bk, const CUtensorMap& ma, const CUtensorMap& mb,
