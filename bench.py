@@ -254,19 +254,39 @@ def side_workloads(args, timer, age, llo, rank, world):
             out[name] = {"GBps": gbps, "ms": ms, "frac_of_measured_hbm": gbps / hbm_peak,
                          "launches_per_eval": launches // steps}
         del vx, x, cases
-        # config 4: matmul fp32 8192^3 on the FFMA pipe (exact path)
+        # config 4: matmul 8192^3 — fp32 on the FFMA pipe (exact path), fp64 on
+        # the DFMA pipe, and the opt-in 3xTF32 tensor-core path (tcgen05)
         m = args.matmul
-        a = np.random.default_rng(5).uniform(-1, 1, (m, m)).astype(np.float32)
-        b = np.random.default_rng(6).uniform(-1, 1, (m, m)).astype(np.float32)
-        va, vb = llo.variable(a, "a"), llo.variable(b, "b")
-        root = age.matmul(va, vb)
-        ms, launches = timer.timed(lambda: llo.evaluate_device(root, F32), max(3, steps // 2), 2)
-        peak, src = ffma_peak()
-        tf = 2.0 * m ** 3 / ms / 1e9
-        out["matmul_f32"] = {"TFLOPs": tf, "ms": ms, "mnk": [m, m, m], "frac_of_ffma_peak": tf / peak,
-                             "ffma_peak_TFLOPs": peak, "peak_source": src,
-                             "launches_per_eval": launches // max(3, steps // 2)}
-        del va, vb, a, b, root
+        gsteps = max(3, steps // 2)
+        fpeak, fsrc = ffma_peak()
+        dpeak = fpeak / 2.0
+        ppath = os.path.join(ROOT, "profiles", "fma_peak.json")
+        if os.path.exists(ppath):
+            with open(ppath) as fh:
+                dpeak = float(json.load(fh).get("dfma_tflops", dpeak))
+        for name, dt, option in (("matmul_f32", np.float32, 0), ("matmul_f32_3xtf32", np.float32, 1),
+                                 ("matmul_f64", np.float64, 0)):
+            a = np.random.default_rng(5).uniform(-1, 1, (m, m)).astype(dt)
+            b = np.random.default_rng(6).uniform(-1, 1, (m, m)).astype(dt)
+            va, vb = llo.variable(a, "a"), llo.variable(b, "b")
+            root = age.matmul(va, vb)
+            llo.set_option("tf32x3", option)
+            try:
+                ms, launches = timer.timed(lambda: llo.evaluate_device(root, np.dtype(dt)), gsteps, 2)
+            finally:
+                llo.set_option("tf32x3", 0)
+            tf = 2.0 * m ** 3 / ms / 1e9
+            entry = {"TFLOPs": tf, "ms": ms, "mnk": [m, m, m], "launches_per_eval": launches // gsteps}
+            if option:
+                entry["path"] = ("opt-in: tcgen05.mma kind::tf32, 3 products per k, TMEM accumulators promoted "
+                                 "every 128 k (results within 1e-6 of sum|a||b|, not bit-identical to FFMA)")
+                entry["speedup_vs_exact"] = tf / out["matmul_f32"]["TFLOPs"]
+            elif dt == np.float32:
+                entry.update({"frac_of_ffma_peak": tf / fpeak, "ffma_peak_TFLOPs": fpeak, "peak_source": fsrc})
+            else:
+                entry.update({"frac_of_dfma_peak": tf / dpeak, "dfma_peak_TFLOPs": dpeak})
+            out[name] = entry
+            del va, vb, a, b, root
     if not args.skip_mlp:
         # config 5: MLP gradient evaluation, batch sharded over the ranks
         from cortenn_b200.sharded import BatchShardedExecutor
@@ -281,6 +301,13 @@ def side_workloads(args, timer, age, llo, rank, world):
         ms, launches = timer.timed(grad_eval, steps, warm)
         flops = workloads.mlp_flops(batch)
         peak, _ = ffma_peak()
+        llo.set_option("tf32x3", 1)
+        try:
+            ms_tc, _ = timer.timed(grad_eval, steps, warm)
+        finally:
+            llo.set_option("tf32x3", 0)
+        out["mlp_grad_eval_3xtf32"] = {"grad_evals_per_s": 1e3 / ms_tc, "ms": ms_tc,
+                                       "path": "opt-in tensor-core GEMMs (tf32x3 = 1); same graph, same allreduce"}
         out["mlp_grad_eval"] = {
             "grad_evals_per_s": 1e3 / ms, "ms": ms, "batch": batch, "rows_per_rank": ex.local_rows(),
             "gemm_TFLOPs_all_ranks": flops / ms / 1e9,

@@ -267,3 +267,22 @@ def test_convolution_through_the_general_path(mode):
     root = age.convolution(img, kernel)
     check(root, F8, scale_tol=100, what="convolution")
     check(llo.derive(root, kernel), F8, scale_tol=100, what="d convolution")
+
+
+def test_tf32x3_option_routes_matmul_to_the_tensor_cores():
+    rng = np.random.default_rng(61)
+    a = rng.uniform(-1, 1, (256, 320)).astype(F4)
+    b = rng.uniform(-1, 1, (320, 384)).astype(F4)
+    root = age.matmul(llo.variable(a, "a"), llo.variable(b, "b"))
+    exact = llo.evaluate(root, np.dtype(F4))
+    llo.set_option("tf32x3", 1)
+    try:
+        before = llo.launch_count()
+        fast = llo.evaluate(root, np.dtype(F4))
+        assert llo.launch_count() - before == 3     # 2 splits + tcgen05 kernel
+    finally:
+        llo.set_option("tf32x3", 0)
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    scale = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+    assert (np.abs(ref - exact) <= 1e-6 * scale).all()
+    assert (np.abs(ref - fast) <= 1e-6 * scale).all()

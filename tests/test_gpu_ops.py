@@ -355,6 +355,34 @@ def test_gemm(ctx, dtype, layout):
         assert (np.abs(expect - got) <= tol * scale).all()
 
 
+@pytest.mark.parametrize("layout", ["nn", "nt", "tn", "tt"])
+@pytest.mark.parametrize("mnk", [(256, 384, 512), (300, 200, 1000), (129, 131, 2085)])
+def test_gemm_3xtf32_tensor_core_path(ctx, layout, mnk):
+    """opt-in precision 1 (tcgen05 kind::tf32, 3 products per k): within 1e-6
+    of sum |a||b| of the float64 product, i.e. as close as the exact FFMA path
+    needs to be (north star: 1e-6 relative for fp32)"""
+    rng = np.random.default_rng(53)
+    M, N, K = mnk
+    A = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+    B = rng.uniform(-1, 1, (K, N)).astype(np.float32)
+    a_store = A if layout[0] == "n" else np.ascontiguousarray(A.T)
+    b_store = B if layout[1] == "n" else np.ascontiguousarray(B.T)
+    a_rs, a_cs = (K, 1) if layout[0] == "n" else (1, M)
+    b_rs, b_cs = (N, 1) if layout[1] == "n" else (1, K)
+    pa = ctx.upload(a_store); pb = ctx.upload(b_store)
+    pc = ctx.alloc(M * N * 4)
+    before = ctx.launch_count()
+    capi.check(ctx.lib.llo_cuda_gemm(ctx.handle, capi.dtype_code(np.float32), M, N, K,
+                                     pa, a_rs, a_cs, pb, b_rs, b_cs, pc, N, 1, 1))
+    assert ctx.launch_count() - before == 3          # 2 operand splits + the tensor-core kernel
+    got = ctx.download(pc, M * N, np.float32).reshape(M, N)
+    for p in (pa, pb, pc):
+        ctx.free(p)
+    expect = A.astype(np.float64) @ B.astype(np.float64)
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)
+    assert (np.abs(expect - got) <= 1e-6 * scale).all()
+
+
 def test_elementwise_program_entry(ctx):
     """llo_cuda_elementwise: out = exp(x) * b[broadcast] + x[transposed]"""
     import ctypes as C
