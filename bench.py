@@ -299,6 +299,14 @@ def side_workloads(args, timer, age, llo, rank, world):
         def grad_eval():
             ex.grad_eval_device(loss, pvars, F32)
         ms, launches = timer.timed(grad_eval, steps, warm)
+        # host time to plan + enqueue one evaluation (no synchronisation): it
+        # must stay below the device time or the GPU starves
+        timer.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            grad_eval()
+        host_ms = (time.perf_counter() - t0) * 1e3 / steps
+        timer.barrier()
         flops = workloads.mlp_flops(batch)
         peak, _ = ffma_peak()
         llo.set_option("tf32x3", 1)
@@ -313,6 +321,7 @@ def side_workloads(args, timer, age, llo, rank, world):
             "gemm_TFLOPs_all_ranks": flops / ms / 1e9,
             "frac_of_ffma_peak": flops / ms / 1e9 / (peak * world),
             "allreduce_bytes": 4 * 1863690, "launches_per_eval": launches // steps,
+            "host_enqueue_ms": host_ms,
             "scaling": "strong (batch 65536 split over the ranks; NCCL allreduce of the packed gradients)"}
     return out
 

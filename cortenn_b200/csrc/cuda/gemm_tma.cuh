@@ -287,28 +287,29 @@ int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 	{
 		return LLO_OK;
 	}
-	// split-K: when the output has fewer tiles than the chip has SMs, the
-	// k-tiles of every output tile are spread over `splits` CTAs and the
-	// partial products are summed in split order by a second pass
+	// split-K: the k-tiles of every output tile may be spread over `splits`
+	// CTAs (partial products summed in split order by a second pass) when
+	// that fills the SMs better.  Cost model in k-tile times: waves of CTAs
+	// x (k-tiles per CTA + ~3 for pipeline fill and epilogue), plus one for
+	// the fold pass.
 	uint32_t ktiles = (uint32_t) ((p.K + BK - 1) / BK);
 	uint32_t splits = 1;
-	if (tiles * 2 <= (uint64_t) ctx->sm_count && ktiles >= 16)
 	{
-		// pick the split count whose grid fills whole waves of SMs best
-		// (ties: fewer splits), between ~1 and ~4 waves
 		uint64_t sms = (uint64_t) ctx->sm_count;
-		uint64_t most = std::min<uint64_t>(ktiles / 8, 64);
-		uint64_t lo = std::max<uint64_t>(2, sms / tiles);
-		uint64_t hi = std::min<uint64_t>(most, (4 * sms + tiles - 1) / tiles);
-		double best = 0;
-		for (uint64_t cand = lo; cand <= hi; ++cand)
+		auto cost = [&] (uint64_t cand) -> uint64_t
 		{
-			uint64_t ctas = tiles * cand;
-			uint64_t waves = (ctas + sms - 1) / sms;
-			double fill = (double) ctas / (double) (waves * sms);
-			if (fill > best + 0.02)
+			uint64_t waves = (tiles * cand + sms - 1) / sms;
+			uint64_t per = (ktiles + cand - 1) / cand;
+			return waves * (per + 3) + (cand > 1 ? 1 : 0);
+		};
+		uint64_t best = cost(1);
+		uint64_t most = std::min<uint64_t>(ktiles / 4, 64);
+		for (uint64_t cand = 2; cand <= most; ++cand)
+		{
+			uint64_t c = cost(cand);
+			if (c * 100 < best * 95) // worth it only for a clear gain
 			{
-				best = fill;
+				best = c;
 				splits = (uint32_t) cand;
 			}
 		}

@@ -1,0 +1,31 @@
+#!/bin/bash
+# Round profile capture (run under gpurun): one ncu --set full capture per hot
+# kernel, exported as text / csv (the .ncu-rep files are too large to return),
+# plus the launch list of a short bench run.
+# usage: tools/capture_profiles.sh <outdir>
+set -u
+OUT=${1:-gpurun_out/profiles}
+mkdir -p "$OUT"
+cap () {  # name, kernel regex, command...
+	local name=$1 regex=$2; shift 2
+	"$@" > "$OUT/plain_$name.log" 2>&1 || { echo "$name: plain run failed"; return; }
+	ncu --set full --clock-control none --import-source on -k "regex:$regex" -c 1 -f \
+		-o /tmp/prof_$name "$@" > "$OUT/ncu_$name.log" 2>&1
+	ncu -i /tmp/prof_$name.ncu-rep --page details > "$OUT/${name}_details.txt" 2>/dev/null
+	ncu -i /tmp/prof_$name.ncu-rep --page raw --csv > "$OUT/${name}_raw.csv" 2>/dev/null
+	echo "$name: done"
+}
+cap chain vm_tile4 python tools/prof_cases.py --case chain --iters 2
+cap exp vm_flat python tools/prof_cases.py --case exp --iters 2
+cap add vm_flat python tools/prof_cases.py --case add --iters 2
+cap permute vm_tile4 python tools/prof_cases.py --case permute --iters 2
+cap rsum_cols fold python tools/prof_cases.py --case rsum_cols --iters 2
+cap rsum_rows fold python tools/prof_cases.py --case rsum_rows --iters 2
+cap rsum_all fold python tools/prof_cases.py --case rsum_all --iters 2
+cap sgemm_nn sgemm_tma python tools/gemm_bench.py --size 4096 --layouts nn --iters 1
+cap dgemm_nn dgemm_tma python tools/gemm_bench.py --size 4096 --dtype f64 --layouts nn --iters 1
+cap tf32x3_nn tf32x3 python tools/gemm_bench.py --size 4096 --precision 1 --layouts nn --iters 1
+python bench.py --steps 3 --warmup 3 --skip-cpu > "$OUT/plain_bench.log" 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
+	--log-file "$OUT/launches_bench.csv" python bench.py --steps 3 --warmup 3 --skip-cpu > "$OUT/ncu_bench.log" 2>&1
+echo "launch list: done"
