@@ -307,9 +307,9 @@ int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 	// enough to amortise one extra pass, a k-contiguous operand is transposed
 	// into scratch first (the products and their order are unchanged).
 	auto relayout = [&] (const T*& base, int64_t& lead, bool& kc,
-		uint64_t rows, uint64_t other) -> int
+		uint64_t rows, uint64_t other, uint64_t threshold) -> int
 	{
-		if (false == kc || other < 1024 || rows < 64 || p.K < 64)
+		if (false == kc || other < threshold || rows < 64 || p.K < 64)
 		{
 			return LLO_OK;
 		}
@@ -326,8 +326,10 @@ int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 		kc = false;
 		return LLO_OK;
 	};
-	LLO_TRY(relayout(A, lead_a, ak, p.M, p.N));
-	LLO_TRY(relayout(B, lead_b, bk, p.N, p.M));
+	// (the pass costs ~8 bytes per operand element and buys ~10% of the
+	// 2 * other flops spent on each of them)
+	LLO_TRY(relayout(A, lead_a, ak, p.M, p.N, 2048));
+	LLO_TRY(relayout(B, lead_b, bk, p.N, p.M, 2048));
 	LLO_TRY(make_ready(ctx, scratch, A, lead_a, ak ? p.M : p.K, ak ? p.K : p.M));
 	LLO_TRY(make_ready(ctx, scratch, B, lead_b, bk ? p.N : p.K, bk ? p.K : p.N));
 	CUtensorMap ma, mb;

@@ -412,17 +412,27 @@ __device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
 {
 	constexpr int V = VmGeom<T>::V;
 	int depth = 0;
+	// every program starts by setting the accumulator (vm_encode): peeled,
+	// so inside the loop the accumulator is only ever updated in place
+	{
+		int arg = p.code[0].arg;
+		if (VM_SRC_IN == (arg >> 4))
+		{
+			loader.load(acc, arg & 15);
+		}
+		else
+		{
+			T c;
+			memcpy(&c, &p.consts[arg & 15], sizeof(T));
+			LLO_VM_EACH(acc[e] = c)
+		}
+	}
 #pragma unroll 1
-	for (int pc = 0; pc < p.ninsns; ++pc)
+	for (int pc = 1; pc < p.ninsns; ++pc)
 	{
 		int sel = p.code[pc].sel;
 		int arg = p.code[pc].arg;
 		int src = arg >> 4;
-		if (VM_S_SET == sel && VM_SRC_IN == src)
-		{
-			loader.load(acc, arg & 15); // straight into the accumulator
-			continue;
-		}
 		T x[V];
 		if (VM_SRC_IN == src)
 		{
