@@ -3,6 +3,7 @@
 /// and the `llo_cuda_elementwise` entry point.
 ///
 
+#include <algorithm>
 #include <cstring>
 #include <utility>
 
@@ -229,6 +230,7 @@ struct Tile4Loader
 
 	const VmParams& p;
 	const T* tiles;          // [slot][64][64], chunk-swizzled
+	const T* alias;          // pair mode: the mirror tile (read straight)
 	uint32_t c0;             // output coordinates of chunk 0; chunk u sits at
 	uint32_t c1;             // (c0 + 32 * (u & 1), c1 + 4 * (u >> 1))
 	uint32_t dim0;
@@ -270,6 +272,29 @@ struct Tile4Loader
 				for (int e = 0; e < 4; ++e)
 				{
 					x[u * 4 + e] = src[e * VM_TS];
+				}
+			}
+			return;
+		}
+		if (VM_IN_ALIAS == in.mode)
+		{
+			// element (c0, c1) of the straight view = [row c1][col c0] of the
+			// mirror tile: row 8 warp + 4 (u >> 1) + s, 16-byte column
+			// 8 (u & 1) + l, swizzled by (row >> 2) & 7
+			int l = threadIdx.x & 7;
+			int s = (threadIdx.x >> 3) & 3;
+			int quad = (threadIdx.x >> 5) * 2;
+#pragma unroll
+			for (int u = 0; u < 4; ++u)
+			{
+				int q = quad + (u >> 1);
+				uint4 tmp = *reinterpret_cast<const uint4*>(alias +
+					(4 * q + s) * VM_TS + (((8 * (u & 1) + l) ^ (q & 7)) << 2));
+				const T* t = reinterpret_cast<const T*>(&tmp);
+#pragma unroll
+				for (int e = 0; e < 4; ++e)
+				{
+					x[u * 4 + e] = t[e];
 				}
 			}
 			return;
@@ -457,13 +482,14 @@ __device__ __forceinline__ void stage_tiles (const VmParams& p, T* tiles,
 /// Run the program for the output tile at (o0, o1) and store it
 template <typename T>
 __device__ __forceinline__ void run_tile (const VmParams& p, const T* tiles,
-	T* spill, uint32_t o0, uint32_t o1, uint32_t brest)
+	T* spill, uint32_t o0, uint32_t o1, uint32_t brest,
+	const T* alias = nullptr)
 {
 	using G = VmGeom<T>;
 	uint32_t dim0 = (uint32_t) p.dims[0];
 	uint32_t dim1 = (uint32_t) p.dims[1];
 	bool full = o0 + VM_TS <= dim0 && o1 + VM_TS <= dim1;
-	Tile4Loader<T> loader = {p, tiles,
+	Tile4Loader<T> loader = {p, tiles, alias,
 		o0 + 4 * (threadIdx.x & 7),
 		o1 + 8 * (threadIdx.x >> 5) + ((threadIdx.x >> 3) & 3),
 		dim0, dim1, brest, full};
@@ -523,9 +549,9 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 		while (tile < p.total_tiles)
 		{
 			uint32_t next = tile + gridDim.x;
+			uint32_t n0 = 0, n1 = 0, nrest = 0;
 			if (next < p.total_tiles)
 			{
-				uint32_t n0, n1, nrest;
 				tile_origin(p, next, n0, n1, nrest);
 				stage_tiles<T,true>(p, tiles + (buf ^ 1) * buf_elems, n0, n1, nrest);
 				asm volatile("cp.async.commit_group;" ::: "memory");
@@ -536,11 +562,13 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 				asm volatile("cp.async.wait_group 0;" ::: "memory");
 			}
 			__syncthreads();
-			tile_origin(p, tile, o0, o1, brest);
 			run_tile<T>(p, tiles + buf * buf_elems, spill, o0, o1, brest);
 			__syncthreads(); // everyone is done with this buffer
 			buf ^= 1;
 			tile = next;
+			o0 = n0;
+			o1 = n1;
+			brest = nrest;
 		}
 	}
 	else
@@ -553,6 +581,104 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 			run_tile<T>(p, tiles, spill, o0, o1, brest);
 			__syncthreads();
 		}
+	}
+}
+
+/// Pair mode (x and permute(x) in one program, square tile grid): a CTA takes
+/// the tile pair {(i,j), (j,i)}, stages the two input tiles ONCE (cp.async,
+/// two slots, double buffered over pairs) and computes both output tiles:
+/// for output (i,j) the transposed operand reads slot 0 transposed and the
+/// straight operand reads slot 1 as it lies; for output (j,i) the slots swap
+/// roles.  Every element of x then crosses L2 -> SM once instead of twice
+/// (the mirror tile order of vm_tile4_kernel already made it cross
+/// DRAM -> L2 once).
+template <typename T>
+__global__ void __launch_bounds__(VM_THREADS, 3)
+vm_pair4_kernel (const __grid_constant__ VmParams p)
+{
+	static_assert(4 == sizeof(T), "4-byte element types only");
+	extern __shared__ __align__(16) unsigned char vm_smem[];
+	T* tiles = reinterpret_cast<T*>(vm_smem);
+	constexpr int SLOT = VM_TS * VM_TS;
+	T* spill = tiles + 4 * SLOT;
+	uint32_t side = p.tiles0;
+	uint32_t pairs = side * (side - 1) / 2;
+	uint32_t per = pairs + side;             // work units per slice of the other dims
+	uint32_t total = p.total_tiles;          // per * (product of the other dims)
+
+	// unit -> (i, j, brest); i == j on the diagonal
+	auto unit_of = [&] (uint32_t unit, uint32_t& i, uint32_t& j, uint32_t& brest)
+	{
+		brest = unit / per;
+		uint32_t q = unit - brest * per;
+		if (q < pairs)
+		{
+			uint32_t jj = (uint32_t) ((1.0f + sqrtf(1.0f + 8.0f * (float) q)) * 0.5f);
+			while (jj * (jj - 1) / 2 > q) { --jj; }
+			while ((jj + 1) * jj / 2 <= q) { ++jj; }
+			j = jj;
+			i = q - jj * (jj - 1) / 2;
+		}
+		else
+		{
+			i = j = q - pairs;
+		}
+	};
+	// slot 0 <- input tile of output (i,j), slot 1 <- input tile of output (j,i)
+	auto stage_pair = [&] (T* buf, uint32_t i, uint32_t j, uint32_t brest)
+	{
+		stage_tiles<T,true>(p, buf, i * VM_TS, j * VM_TS, brest);
+		if (i != j)
+		{
+			stage_tiles<T,true>(p, buf + SLOT, j * VM_TS, i * VM_TS, brest);
+		}
+	};
+
+	uint32_t unit = blockIdx.x;
+	uint32_t i, j, brest;
+	if (unit >= total)
+	{
+		return;
+	}
+	unit_of(unit, i, j, brest);
+	stage_pair(tiles, i, j, brest);
+	asm volatile("cp.async.commit_group;" ::: "memory");
+	int buf = 0;
+	while (unit < total)
+	{
+		uint32_t next = unit + gridDim.x;
+		uint32_t ni = 0, nj = 0, nrest = 0;
+		if (next < total)
+		{
+			unit_of(next, ni, nj, nrest);
+			stage_pair(tiles + (buf ^ 1) * 2 * SLOT, ni, nj, nrest);
+			asm volatile("cp.async.commit_group;" ::: "memory");
+			asm volatile("cp.async.wait_group 1;" ::: "memory");
+		}
+		else
+		{
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+		}
+		__syncthreads();
+		T* slot0 = tiles + buf * 2 * SLOT;
+		T* slot1 = slot0 + SLOT;
+		int halves = (i == j) ? 1 : 2;
+#pragma unroll 1
+		for (int h = 0; h < halves; ++h)
+		{
+			// h = 0: output (i,j) from slot 0 transposed + slot 1 straight;
+			// h = 1: output (j,i) with the slots' roles swapped
+			const T* self = h ? slot1 : slot0;
+			const T* other = (i == j) ? slot0 : (h ? slot0 : slot1);
+			run_tile<T>(p, self, spill, (h ? j : i) * VM_TS, (h ? i : j) * VM_TS,
+				brest, other);
+		}
+		__syncthreads(); // everyone is done with this buffer
+		buf ^= 1;
+		unit = next;
+		i = ni;
+		j = nj;
+		brest = nrest;
 	}
 }
 
@@ -1025,6 +1151,43 @@ static int plan_tiles (VmParams& p, size_t esize, int chunk, int tile0, int tile
 		}
 	}
 	p.tile_aligned = aligned ? 1 : 0;
+	p.pair_mode = 0;
+	if (aligned && 4 == esize && p.mirror && 1 == nstaged &&
+		p.dims[0] == p.dims[1])
+	{
+		// a straight view of the same buffer whose strides mirror the staged
+		// (transposed) view's: f(x, permute(x)).  vm_pair4_kernel reads it
+		// from the mirror tile in shared memory.
+		int t = -1;
+		for (int k = 0; k < p.ninputs; ++k)
+		{
+			if (VM_IN_TILE == p.in[k].mode)
+			{
+				t = k;
+			}
+		}
+		for (int k = 0; k < p.ninputs && t >= 0; ++k)
+		{
+			VmInput& in = p.in[k];
+			const VmInput& tr = p.in[t];
+			if (VM_IN_STRIDED != in.mode || in.data != tr.data ||
+				in.offset != tr.offset || 1 != in.stride[0] ||
+				in.stride[1] != tr.stride[0])
+			{
+				continue;
+			}
+			bool same = true;
+			for (int d = 2; d < p.ndims; ++d)
+			{
+				same = same && in.stride[d] == tr.stride[d];
+			}
+			if (same)
+			{
+				in.mode = VM_IN_ALIAS;
+				p.pair_mode = 1;
+			}
+		}
+	}
 	return nstaged;
 }
 
@@ -1053,6 +1216,21 @@ static int launch_tile (llo_cuda_ctx* ctx, VmParams& p, int nstaged,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
 			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_tile4_kernel<T,false>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+		}
+		if (p.pair_mode)
+		{
+			// work units: tile pairs + diagonal tiles, per slice of the other dims
+			uint64_t side = p.tiles0;
+			uint64_t units = (uint64_t) p.total_tiles / (side * side) *
+				(side * (side - 1) / 2 + side);
+			p.total_tiles = (uint32_t) units;
+			size_t psmem = (size_t) 4 * VM_TS * VM_TS * sizeof(T) + spill;
+			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_pair4_kernel<T>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+			unsigned pblocks = (unsigned) std::min<uint64_t>(units,
+				(uint64_t) ctx->sm_count * 3);
+			vm_pair4_kernel<T><<<pblocks, VM_THREADS, psmem, ctx->stream>>>(p);
+			return launched(ctx, "vm_pair4_kernel");
 		}
 		if (p.tile_aligned)
 		{

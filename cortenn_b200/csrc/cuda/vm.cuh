@@ -44,6 +44,8 @@ enum VmInputMode
 	VM_IN_STRIDED,     // data[offset + sum_d c_d * stride[d]]
 	VM_IN_INDEXED,     // data[index[i]]  (general-map gather table)
 	VM_IN_TILE,        // strided, staged through a transposing smem tile
+	VM_IN_ALIAS,       // the straight view of a buffer whose transposed view is
+	                   // VM_IN_TILE: read from the mirror tile already in smem
 };
 
 struct VmInput
@@ -152,6 +154,8 @@ struct VmParams
 	int32_t tile_aligned;   // every staged row start is 16-byte aligned
 	int32_t mirror;         // square tile grid: tile (i,j) runs next to (j,i)
 	uint32_t total_tiles;   // tiles of the whole launch (persistent kernels)
+	int32_t pair_mode;      // one CTA computes output tiles (i,j) and (j,i) from
+	                        // the two input tiles it staged once (vm_pair4_kernel)
 	uint64_t dims[LLO_RANK];
 	int64_t out_stride[LLO_RANK]; // dense strides of the collapsed dims
 	FastDiv div[LLO_RANK];

@@ -286,3 +286,30 @@ def test_tf32x3_option_routes_matmul_to_the_tensor_cores():
     scale = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
     assert (np.abs(ref - exact) <= 1e-6 * scale).all()
     assert (np.abs(ref - fast) <= 1e-6 * scale).all()
+
+
+@pytest.mark.parametrize("side,extra", [(200, ()), (256, ()), (130, (3,)), (64, ()), (65, (2,))])
+def test_program_with_a_tensor_and_its_transpose(side, extra):
+    """f(x, permute(x)): the tile engine computes output tiles (i,j) and (j,i)
+    from the two input tiles it staged once (vm_pair4_kernel); ragged sizes,
+    extra dims and the single-tile case included"""
+    rng = np.random.default_rng(71)
+    shape = extra + (side, side)                      # numpy order: ade dims 0, 1 are the last two
+    x = rng.uniform(0.5, 2.0, shape).astype(F4)
+    b = rng.uniform(0.5, 2.0, (side,)).astype(F4)
+    vx, vb = llo.variable(x, "x"), llo.variable(b, "b")
+    ext = age.extend(vb, 1, list(reversed(shape[:-1])))
+    order = [1, 0] + list(range(2, len(shape)))
+    root = age.add(age.mul(age.exp(vx), ext), age.permute(vx, order))
+    got = llo.evaluate(root, np.dtype(F4))
+    want = oracle.evaluate(root, np.dtype(F4))
+    assert got.shape == want.shape == x.shape
+    assert np.abs(got.astype(np.float64) - want).max() <= 1e-6 * np.abs(want).max()
+    expect = (np.exp(x.astype(np.float64)) * b) + np.swapaxes(x, -1, -2)
+    assert np.abs(got - expect).max() <= 2e-6 * np.abs(expect).max()
+    # integer: bit-exact
+    xi = rng.integers(-50, 50, shape).astype(np.int32)
+    vi = llo.variable(xi, "xi")
+    rooti = age.sub(age.mul(vi, vi), age.permute(vi, order))
+    np.testing.assert_array_equal(llo.evaluate(rooti, np.dtype(np.int32)),
+                                  xi * xi - np.swapaxes(xi, -1, -2))
