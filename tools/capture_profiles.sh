@@ -15,7 +15,7 @@ cap () {  # name, kernel regex, command...
 	ncu -i /tmp/prof_$name.ncu-rep --page raw --csv > "$OUT/${name}_raw.csv" 2>/dev/null
 	echo "$name: done"
 }
-cap chain vm_tile4 python tools/prof_cases.py --case chain --iters 2
+cap chain vm_pair4 python tools/prof_cases.py --case chain --iters 2
 cap exp vm_flat python tools/prof_cases.py --case exp --iters 2
 cap add vm_flat python tools/prof_cases.py --case add --iters 2
 cap permute vm_tile4 python tools/prof_cases.py --case permute --iters 2
