@@ -131,6 +131,15 @@ inline uint64_t n_elems (const uint64_t shape[LLO_RANK])
 
 /// Dispatch a generic lambda on the C type of `dtype`:
 /// LLO_DISPATCH_DTYPE(dtype, T, { kernel<T><<<...>>>(...); })
+#ifdef LLO_DEV_FLOAT_ONLY
+// development builds only (fast ptxas / SASS turnaround): float kernels
+#define LLO_DISPATCH_DTYPE(DTYPE, T, ...)\
+	switch (DTYPE)\
+	{\
+		case LLO_DT_FLOAT: { using T = float; __VA_ARGS__ } break;\
+		default: return llo_cuda::fail(LLO_ERR_FATAL, "executing bad type %d", (int) (DTYPE));\
+	}
+#else
 #define LLO_DISPATCH_DTYPE(DTYPE, T, ...)\
 	switch (DTYPE)\
 	{\
@@ -146,6 +155,7 @@ inline uint64_t n_elems (const uint64_t shape[LLO_RANK])
 		case LLO_DT_UINT64: { using T = uint64_t; __VA_ARGS__ } break;\
 		default: return llo_cuda::fail(LLO_ERR_FATAL, "executing bad type %d", (int) (DTYPE));\
 	}
+#endif
 
 /// Scratch device allocation released (stream-ordered) at scope exit
 struct Scratch final

@@ -190,13 +190,17 @@ vm_tile_kernel (const __grid_constant__ VmParams p)
 //
 // 64 x 64 tile.  The staged (transposed) input tile is copied as it lies in
 // memory, 16 bytes per cp.async, into smem [r0][p] (r0: output dim 0, p: the
-// input's contiguous direction) with the 16-byte chunk index XORed by
-// (r0 >> 2) & 7.  The compute phase reads it transposed: per warp
-// instruction 8 lanes x 4 consecutive r0 (one chunk column each, spread by
-// the XOR) times 4 lanes of consecutive p (the 4 words of one chunk): 32
-// distinct banks.  Chunk u of a thread: row p = 4 * quad + s, columns
-// 32 * half + 4 * l .. +4 with l = t & 7, s = (t >> 3) & 3, (quad, half)
-// from (warp, u).
+// input's contiguous direction = output dim 1) with the 16-byte chunk index
+// XORed by (r0 >> 2) & 7.
+// Compute phase: the 256 threads form a 16 x 16 grid, thread (tx, ty) =
+// (t & 15, t >> 4) owns the 4 x 4 outputs c0 = 4 tx .. +3 (dim 0) by
+// c1 = 4 ty .. +3 (dim 1); element u * 4 + e of its value set is
+// (c0 + e, c1 + u), i.e. chunk u is a 128-bit piece of output row c1 + u (a
+// warp covers two 256-byte row segments per chunk: full sectors on the straight
+// loads and on the stores).  The transposed operand is four LDS.128 -- row
+// 4 tx + e, chunk ty of the staged tile -- whose words are the four c1 of
+// element e (a transpose in register names only); the XOR spreads the 8
+// lanes of an LDS phase (8 consecutive tx, one ty) over all 8 chunk columns.
 
 constexpr int VM_TS = 64;
 
@@ -206,6 +210,13 @@ __device__ __forceinline__ void cp_async16 (void* smem_dst, const void* src,
 	uint32_t dst = (uint32_t) __cvta_generic_to_shared(smem_dst);
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
 		:: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+/// full 16-byte copy to a shared-window address
+__device__ __forceinline__ void cp_async16_full (uint32_t dst, const void* src)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+		:: "r"(dst), "l"(src) : "memory");
 }
 
 /// 32-bit form of rest_offset (the tile launch requires 32-bit addressing)
@@ -223,33 +234,53 @@ __device__ __forceinline__ int32_t rest_offset32 (const VmParams& p,
 	return off;
 }
 
-template <typename T>
+/// Thread-constant read positions inside a staged tile (elements)
+struct Tile4Thread
+{
+	uint32_t tx4;        // 4 tx: first dim-0 coordinate inside the tile
+	uint32_t ty4;        // 4 ty: first dim-1 coordinate inside the tile
+	uint32_t tile_off;   // transposed read, e = 0 (row 4 tx, chunk ty); +64 per e
+	uint32_t alias_off;  // straight read of the mirror tile, u = 0 (row 4 ty, chunk tx)
+};
+
+__device__ __forceinline__ Tile4Thread tile4_thread ()
+{
+	uint32_t tx = threadIdx.x & 15;
+	uint32_t ty = threadIdx.x >> 4;
+	Tile4Thread th;
+	th.tx4 = 4 * tx;
+	th.ty4 = 4 * ty;
+	th.tile_off = 4 * tx * VM_TS + ((ty ^ (tx & 7)) << 2);
+	th.alias_off = 4 * ty * VM_TS + ((tx ^ (ty & 7)) << 2);
+	return th;
+}
+
+template <typename T, bool FULL>
 struct Tile4Loader
 {
 	using G = VmGeom<T>;
 
 	const VmParams& p;
-	const T* tiles;          // [slot][64][64], chunk-swizzled
-	const T* alias;          // pair mode: the mirror tile (read straight)
-	uint32_t c0;             // output coordinates of chunk 0; chunk u sits at
-	uint32_t c1;             // (c0 + 32 * (u & 1), c1 + 4 * (u >> 1))
+	const T* tile_rd;        // tiles + tile_off; slot k at + k * 64 * 64
+	const T* alias_rd;       // pair mode: mirror tile + alias_off
+	uint32_t c0;             // output coordinates of element 0; element u * 4 + e
+	uint32_t c1;             // sits at (c0 + e, c1 + u)
 	uint32_t dim0;
 	uint32_t dim1;
 	uint32_t brest;
-	bool full;               // the whole tile lies inside the output
+	bool full;               // FULL = false: the whole tile lies inside the output
 
 	__device__ __forceinline__ int valid (int u) const
 	{
-		if (full)
+		if (FULL || full)
 		{
 			return 4;
 		}
-		uint32_t a = c0 + 32 * (u & 1);
-		if (c1 + 4 * (u >> 1) >= dim1 || a >= dim0)
+		if (c1 + u >= dim1 || c0 >= dim0)
 		{
 			return 0;
 		}
-		uint32_t left = dim0 - a;
+		uint32_t left = dim0 - c0;
 		return left < 4u ? (int) left : 4;
 	}
 
@@ -258,20 +289,16 @@ struct Tile4Loader
 		const VmInput& in = p.in[k];
 		if (VM_IN_TILE == in.mode)
 		{
-			int l = threadIdx.x & 7;
-			int s = (threadIdx.x >> 3) & 3;
-			int quad = (threadIdx.x >> 5) * 2;   // of chunks 0/1; chunks 2/3: + 1
-			const T* tile = tiles + in.vec_ok * VM_TS * VM_TS +
-				4 * l * VM_TS + s;
+			const T* src = tile_rd + in.vec_ok * VM_TS * VM_TS;
 #pragma unroll
-			for (int u = 0; u < 4; ++u)
+			for (int e = 0; e < 4; ++e)
 			{
-				const T* src = tile + 32 * (u & 1) * VM_TS +
-					(((quad + (u >> 1)) ^ l) << 2);
+				uint4 tmp = *reinterpret_cast<const uint4*>(src + e * VM_TS);
+				const T* t = reinterpret_cast<const T*>(&tmp);
 #pragma unroll
-				for (int e = 0; e < 4; ++e)
+				for (int u = 0; u < 4; ++u)
 				{
-					x[u * 4 + e] = src[e * VM_TS];
+					x[u * 4 + e] = t[u];
 				}
 			}
 			return;
@@ -279,17 +306,11 @@ struct Tile4Loader
 		if (VM_IN_ALIAS == in.mode)
 		{
 			// element (c0, c1) of the straight view = [row c1][col c0] of the
-			// mirror tile: row 8 warp + 4 (u >> 1) + s, 16-byte column
-			// 8 (u & 1) + l, swizzled by (row >> 2) & 7
-			int l = threadIdx.x & 7;
-			int s = (threadIdx.x >> 3) & 3;
-			int quad = (threadIdx.x >> 5) * 2;
+			// mirror tile
 #pragma unroll
 			for (int u = 0; u < 4; ++u)
 			{
-				int q = quad + (u >> 1);
-				uint4 tmp = *reinterpret_cast<const uint4*>(alias +
-					(4 * q + s) * VM_TS + (((8 * (u & 1) + l) ^ (q & 7)) << 2));
+				uint4 tmp = *reinterpret_cast<const uint4*>(alias_rd + u * VM_TS);
 				const T* t = reinterpret_cast<const T*>(&tmp);
 #pragma unroll
 				for (int e = 0; e < 4; ++e)
@@ -306,13 +327,29 @@ struct Tile4Loader
 			(int32_t) c0 * s0 + (int32_t) c1 * s1;
 		if (1 == s0)
 		{
-			if (full && in.vec_ok)
+			if ((FULL || full) && in.vec_ok)
 			{
+				if (0 == s1)
+				{
+					// broadcast along dim 1: the four chunks are the same 16 bytes
+					uint4 tmp = __ldg(reinterpret_cast<const uint4*>(data + off));
+					const T* t = reinterpret_cast<const T*>(&tmp);
+#pragma unroll
+					for (int u = 0; u < 4; ++u)
+					{
+#pragma unroll
+						for (int e = 0; e < 4; ++e)
+						{
+							x[u * 4 + e] = t[e];
+						}
+					}
+					return;
+				}
 #pragma unroll
 				for (int u = 0; u < 4; ++u)
 				{
 					uint4 tmp = __ldg(reinterpret_cast<const uint4*>(
-						data + off + 32 * (u & 1) + 4 * (u >> 1) * s1));
+						data + off + u * s1));
 					const T* t = reinterpret_cast<const T*>(&tmp);
 #pragma unroll
 					for (int e = 0; e < 4; ++e)
@@ -325,21 +362,18 @@ struct Tile4Loader
 #pragma unroll
 			for (int u = 0; u < 4; ++u)
 			{
-				load_chunk<T,4,false>(x + u * 4,
-					data + off + 32 * (u & 1) + 4 * (u >> 1) * s1,
+				load_chunk<T,4,false>(x + u * 4, data + off + u * s1,
 					in.vec_ok, valid(u));
 			}
 		}
 		else if (0 == s0)
 		{
 #pragma unroll
-			for (int u = 0; u < 4; u += 2)
+			for (int u = 0; u < 4; ++u)
 			{
-				// chunks u and u + 1 differ in dim 0 only: same element
-				T v = (valid(u) > 0 || valid(u + 1) > 0) ?
-					__ldg(data + off + 4 * (u >> 1) * s1) : T();
+				T v = valid(u) > 0 ? __ldg(data + off + u * s1) : T();
 #pragma unroll
-				for (int e = 0; e < 8; ++e)
+				for (int e = 0; e < 4; ++e)
 				{
 					x[u * 4 + e] = v;
 				}
@@ -351,7 +385,7 @@ struct Tile4Loader
 			for (int u = 0; u < 4; ++u)
 			{
 				int ok = valid(u);
-				const T* src = data + off + 32 * (u & 1) * s0 + 4 * (u >> 1) * s1;
+				const T* src = data + off + u * s1;
 #pragma unroll
 				for (int e = 0; e < 4; ++e)
 				{
@@ -480,25 +514,23 @@ __device__ __forceinline__ void stage_tiles (const VmParams& p, T* tiles,
 }
 
 /// Run the program for the output tile at (o0, o1) and store it
-template <typename T>
-__device__ __forceinline__ void run_tile (const VmParams& p, const T* tiles,
-	T* spill, uint32_t o0, uint32_t o1, uint32_t brest,
-	const T* alias = nullptr)
+template <typename T, bool FULL>
+__device__ __forceinline__ void run_tile (const VmParams& p,
+	const Tile4Thread& th, const T* tiles, T* spill,
+	uint32_t o0, uint32_t o1, uint32_t brest, const T* alias = nullptr)
 {
 	using G = VmGeom<T>;
-	uint32_t dim0 = (uint32_t) p.dims[0];
-	uint32_t dim1 = (uint32_t) p.dims[1];
-	bool full = o0 + VM_TS <= dim0 && o1 + VM_TS <= dim1;
-	Tile4Loader<T> loader = {p, tiles, alias,
-		o0 + 4 * (threadIdx.x & 7),
-		o1 + 8 * (threadIdx.x >> 5) + ((threadIdx.x >> 3) & 3),
-		dim0, dim1, brest, full};
+	Tile4Loader<T,FULL> loader = {p, tiles + th.tile_off,
+		alias + th.alias_off, o0 + th.tx4, o1 + th.ty4,
+		(uint32_t) p.dims[0], (uint32_t) p.dims[1], brest,
+		FULL || (o0 + VM_TS <= (uint32_t) p.dims[0] &&
+			o1 + VM_TS <= (uint32_t) p.dims[1])};
 	T acc[G::V];
 	vm_exec<T>(acc, p, loader, spill);
 	int32_t os1 = (int32_t) p.out_stride[1];
 	T* out = static_cast<T*>(p.out) + rest_offset32(p, p.out_stride, brest) +
 		(int32_t) loader.c0 + (int32_t) loader.c1 * os1;
-	if (full && p.out_vec_ok)
+	if (loader.full && p.out_vec_ok)
 	{
 #pragma unroll
 		for (int u = 0; u < 4; ++u)
@@ -510,7 +542,7 @@ __device__ __forceinline__ void run_tile (const VmParams& p, const T* tiles,
 			{
 				t[e] = acc[u * 4 + e];
 			}
-			__stcs(reinterpret_cast<uint4*>(out + 32 * (u & 1) + 4 * (u >> 1) * os1), tmp);
+			__stcs(reinterpret_cast<uint4*>(out + u * os1), tmp);
 		}
 		return;
 	}
@@ -520,8 +552,7 @@ __device__ __forceinline__ void run_tile (const VmParams& p, const T* tiles,
 		int ok = loader.valid(u);
 		if (ok > 0)
 		{
-			store_chunk<T,4>(out + 32 * (u & 1) + 4 * (u >> 1) * os1,
-				acc + u * 4, p.out_vec_ok, ok);
+			store_chunk<T,4>(out + u * os1, acc + u * 4, p.out_vec_ok, ok);
 		}
 	}
 }
@@ -538,6 +569,7 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 	T* tiles = reinterpret_cast<T*>(vm_smem);
 	const int buf_elems = p.nstaged * VM_TS * VM_TS;
 	T* spill = tiles + (ALIGNED ? 2 : 1) * buf_elems;
+	const Tile4Thread th = tile4_thread();
 	uint32_t o0, o1, brest;
 	if (ALIGNED)
 	{
@@ -562,7 +594,7 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 				asm volatile("cp.async.wait_group 0;" ::: "memory");
 			}
 			__syncthreads();
-			run_tile<T>(p, tiles + buf * buf_elems, spill, o0, o1, brest);
+			run_tile<T,false>(p, th, tiles + buf * buf_elems, spill, o0, o1, brest);
 			__syncthreads(); // everyone is done with this buffer
 			buf ^= 1;
 			tile = next;
@@ -578,20 +610,21 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 			tile_origin(p, tile, o0, o1, brest);
 			stage_tiles<T,false>(p, tiles, o0, o1, brest);
 			__syncthreads();
-			run_tile<T>(p, tiles, spill, o0, o1, brest);
+			run_tile<T,false>(p, th, tiles, spill, o0, o1, brest);
 			__syncthreads();
 		}
 	}
 }
 
-/// Pair mode (x and permute(x) in one program, square tile grid): a CTA takes
-/// the tile pair {(i,j), (j,i)}, stages the two input tiles ONCE (cp.async,
-/// two slots, double buffered over pairs) and computes both output tiles:
-/// for output (i,j) the transposed operand reads slot 0 transposed and the
-/// straight operand reads slot 1 as it lies; for output (j,i) the slots swap
-/// roles.  Every element of x then crosses L2 -> SM once instead of twice
-/// (the mirror tile order of vm_tile4_kernel already made it cross
-/// DRAM -> L2 once).
+/// Pair mode (x and permute(x) in one program, square grid of full tiles): a
+/// CTA takes the tile pair {(i,j), (j,i)}, stages the two input tiles ONCE
+/// (cp.async, two slots, double buffered over pairs) and computes both output
+/// tiles: for output (i,j) the transposed operand reads slot 0 transposed and
+/// the straight operand reads slot 1 as it lies; for output (j,i) the slots
+/// swap roles.  Every element of x then crosses DRAM -> L2 -> SM once.
+/// Staging addresses are affine in the tile indices: everything that depends
+/// on the thread only (source offset inside a tile, swizzled destination) is
+/// computed once per kernel.
 template <typename T>
 __global__ void __launch_bounds__(VM_THREADS, 3)
 vm_pair4_kernel (const __grid_constant__ VmParams p)
@@ -601,10 +634,24 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 	T* tiles = reinterpret_cast<T*>(vm_smem);
 	constexpr int SLOT = VM_TS * VM_TS;
 	T* spill = tiles + 4 * SLOT;
-	uint32_t side = p.tiles0;
-	uint32_t pairs = side * (side - 1) / 2;
-	uint32_t per = pairs + side;             // work units per slice of the other dims
-	uint32_t total = p.total_tiles;          // per * (product of the other dims)
+	const uint32_t side = p.tiles0;
+	const uint32_t pairs = side * (side - 1) / 2;
+	const uint32_t per = pairs + side;       // work units per slice of the other dims
+	const uint32_t total = p.total_tiles;    // per * (product of the other dims)
+	const Tile4Thread th = tile4_thread();
+
+	// staging: thread t copies 16-byte column t % 16 of rows t / 16 + 16 j
+	const VmInput& tin = p.in[p.tile_input];
+	const int32_t s0 = (int32_t) tin.stride[0];
+	const uint32_t r0 = threadIdx.x >> 4;
+	const uint32_t pc = threadIdx.x & 15;
+	const T* const tsrc = static_cast<const T*>(tin.data) + tin.offset +
+		(int32_t) r0 * s0 + (int32_t) pc * 4;
+	const int64_t rstep = (int64_t) 16 * s0;
+	const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(tiles);
+	// rows r0 + 16 j: the swizzle key (r0 >> 2) + 4 j flips bit 2 for odd j
+	const uint32_t dst_even = r0 * (VM_TS * 4) + ((pc ^ (r0 >> 2)) << 4);
+	const uint32_t dst_odd = dst_even ^ 64u;
 
 	// unit -> (i, j, brest); i == j on the diagonal
 	auto unit_of = [&] (uint32_t unit, uint32_t& i, uint32_t& j, uint32_t& brest)
@@ -624,13 +671,27 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 			i = j = q - pairs;
 		}
 	};
-	// slot 0 <- input tile of output (i,j), slot 1 <- input tile of output (j,i)
-	auto stage_pair = [&] (T* buf, uint32_t i, uint32_t j, uint32_t brest)
+	// input tile of output tile (ti, tj) -> the slot at shared address `slot`
+	auto stage_one = [&] (uint32_t slot, uint32_t ti, uint32_t tj, int32_t rest)
 	{
-		stage_tiles<T,true>(p, buf, i * VM_TS, j * VM_TS, brest);
+		const T* src = tsrc + (rest + (int32_t) (ti * VM_TS) * s0 +
+			(int32_t) (tj * VM_TS));
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+		{
+			cp_async16_full(slot + ((j & 1) ? dst_odd : dst_even) +
+				j * (16 * VM_TS * 4), src + j * rstep);
+		}
+	};
+	// slot 0 <- input tile of output (i,j), slot 1 <- input tile of output (j,i)
+	auto stage_pair = [&] (int buf, uint32_t i, uint32_t j, uint32_t brest)
+	{
+		int32_t rest = rest_offset32(p, tin.stride, brest);
+		uint32_t slot = smem0 + (uint32_t) buf * (2 * SLOT * 4);
+		stage_one(slot, i, j, rest);
 		if (i != j)
 		{
-			stage_tiles<T,true>(p, buf + SLOT, j * VM_TS, i * VM_TS, brest);
+			stage_one(slot + SLOT * 4, j, i, rest);
 		}
 	};
 
@@ -641,7 +702,7 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 		return;
 	}
 	unit_of(unit, i, j, brest);
-	stage_pair(tiles, i, j, brest);
+	stage_pair(0, i, j, brest);
 	asm volatile("cp.async.commit_group;" ::: "memory");
 	int buf = 0;
 	while (unit < total)
@@ -651,7 +712,7 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 		if (next < total)
 		{
 			unit_of(next, ni, nj, nrest);
-			stage_pair(tiles + (buf ^ 1) * 2 * SLOT, ni, nj, nrest);
+			stage_pair(buf ^ 1, ni, nj, nrest);
 			asm volatile("cp.async.commit_group;" ::: "memory");
 			asm volatile("cp.async.wait_group 1;" ::: "memory");
 		}
@@ -661,17 +722,16 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 		}
 		__syncthreads();
 		T* slot0 = tiles + buf * 2 * SLOT;
-		T* slot1 = slot0 + SLOT;
+		T* slot1 = (i == j) ? slot0 : slot0 + SLOT;
 		int halves = (i == j) ? 1 : 2;
 #pragma unroll 1
 		for (int h = 0; h < halves; ++h)
 		{
 			// h = 0: output (i,j) from slot 0 transposed + slot 1 straight;
 			// h = 1: output (j,i) with the slots' roles swapped
-			const T* self = h ? slot1 : slot0;
-			const T* other = (i == j) ? slot0 : (h ? slot0 : slot1);
-			run_tile<T>(p, self, spill, (h ? j : i) * VM_TS, (h ? i : j) * VM_TS,
-				brest, other);
+			run_tile<T,true>(p, th, h ? slot1 : slot0, spill,
+				(h ? j : i) * VM_TS, (h ? i : j) * VM_TS, brest,
+				h ? slot0 : slot1);
 		}
 		__syncthreads(); // everyone is done with this buffer
 		buf ^= 1;
@@ -1152,8 +1212,9 @@ static int plan_tiles (VmParams& p, size_t esize, int chunk, int tile0, int tile
 	}
 	p.tile_aligned = aligned ? 1 : 0;
 	p.pair_mode = 0;
+	p.tile_input = 0;
 	if (aligned && 4 == esize && p.mirror && 1 == nstaged &&
-		p.dims[0] == p.dims[1])
+		p.dims[0] == p.dims[1] && 0 == p.dims[0] % (uint64_t) tile0)
 	{
 		// a straight view of the same buffer whose strides mirror the staged
 		// (transposed) view's: f(x, permute(x)).  vm_pair4_kernel reads it
@@ -1164,6 +1225,7 @@ static int plan_tiles (VmParams& p, size_t esize, int chunk, int tile0, int tile
 			if (VM_IN_TILE == p.in[k].mode)
 			{
 				t = k;
+				p.tile_input = k;
 			}
 		}
 		for (int k = 0; k < p.ninputs && t >= 0; ++k)

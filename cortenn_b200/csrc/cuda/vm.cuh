@@ -156,6 +156,7 @@ struct VmParams
 	uint32_t total_tiles;   // tiles of the whole launch (persistent kernels)
 	int32_t pair_mode;      // one CTA computes output tiles (i,j) and (j,i) from
 	                        // the two input tiles it staged once (vm_pair4_kernel)
+	int32_t tile_input;     // pair mode: index of the staged input
 	uint64_t dims[LLO_RANK];
 	int64_t out_stride[LLO_RANK]; // dense strides of the collapsed dims
 	FastDiv div[LLO_RANK];
