@@ -386,7 +386,7 @@ def run_own(args, rank, local_rank, world):
     roofline = {"bound": "hbm", "achieved": nbytes / ms_step / 1e6, "peak": peak, "unit": "GB/s",
                 "frac": nbytes / ms_step / 1e6 / peak, "traffic": None, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": nbytes / ms_step / 1e6 / 8000.0,
-                "kernel": "vm_tile4_kernel<float,true> (the whole step is %d launch per evaluation)" % per_eval,
+                "kernel": "vm_pair4_kernel<float> (the whole step is %d launch per evaluation)" % per_eval,
                 "algorithmic_bytes_per_launch": nbytes}
     traffic_path = os.path.join(ROOT, "profiles", "chain_traffic.json")
     if os.path.exists(traffic_path):

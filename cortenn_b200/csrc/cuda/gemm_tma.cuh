@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <utility>
 
 #include <cuda.h>
@@ -37,7 +38,30 @@ struct GemmArgs
 	// into the partial product C + y * split_stride
 	uint32_t kt_per_split;
 	int64_t split_stride;
+	// persistent kernels: work units [0, full_tiles) are whole tiles summed
+	// over every k-tile straight into C; each tile >= full_tiles (the last,
+	// partial round of the grid) is cut into tail_splits ranges of
+	// kt_per_split k-tiles whose partial products go to
+	// part[(tile - full_tiles) * tail_splits + split][BM][BN] and are summed
+	// in split order by tile_fold_kernel
+	uint32_t ktiles;
+	uint32_t full_tiles;
+	uint32_t tail_splits;
+	T* part;
 };
+
+/// Tile number -> tile coordinates: walk GROUP tile-rows per tile-column so
+/// the CTAs in flight share their A panels and B panels in L2
+__host__ __device__ __forceinline__ void tile_coords (uint32_t tile,
+	uint32_t tiles_m, uint32_t tiles_n, uint32_t& tile_m, uint32_t& tile_n)
+{
+	constexpr uint32_t GROUP = 16;
+	uint32_t per_group = GROUP * tiles_n;
+	uint32_t first_m = (tile / per_group) * GROUP;
+	uint32_t gsize = tiles_m - first_m < GROUP ? tiles_m - first_m : GROUP;
+	tile_m = first_m + (tile % per_group) % gsize;
+	tile_n = (tile % per_group) / gsize;
+}
 
 __device__ __forceinline__ uint32_t smem_u32 (const void* p)
 {
@@ -187,6 +211,64 @@ splitk_fold_kernel (T* __restrict__ C, int64_t c_rs,
 	C[m * c_rs + n] = acc;
 }
 
+/// Second pass of the persistent kernels' tail split: C tile = sum over s
+/// (ascending) of part[(t * splits + s)][BM][BN]; one CTA per tail tile
+template <typename T, int BM, int BN>
+__global__ void __launch_bounds__(256)
+tile_fold_kernel (T* __restrict__ C, int64_t c_rs, const T* __restrict__ part,
+	uint32_t M, uint32_t N, uint32_t tiles_m, uint32_t tiles_n,
+	uint32_t full_tiles, uint32_t splits, uint32_t vec_store)
+{
+	constexpr int E = 16 / (int) sizeof(T);
+	using V = typename std::conditional<8 == sizeof(T), double2, float4>::type;
+	uint32_t t = blockIdx.x;
+	uint32_t tile_m, tile_n;
+	tile_coords(full_tiles + t, tiles_m, tiles_n, tile_m, tile_n);
+	const T* base = part + (size_t) t * splits * (BM * BN);
+	// blockIdx.y strides over the tile's vectors with the threads
+	for (uint32_t i = blockIdx.y * 256 + threadIdx.x; i < BM * BN / E;
+		i += 256 * gridDim.y)
+	{
+		uint32_t r = i / (BN / E);
+		uint32_t c = (i % (BN / E)) * E;
+		uint32_t m = tile_m * BM + r;
+		uint32_t n = tile_n * BN + c;
+		if (m >= M || n >= N)
+		{
+			continue;
+		}
+		V acc = __ldcs(reinterpret_cast<const V*>(base + r * BN + c));
+		T* a = reinterpret_cast<T*>(&acc);
+		for (uint32_t s = 1; s < splits; ++s)
+		{
+			V nxt = __ldcs(reinterpret_cast<const V*>(
+				base + (size_t) s * (BM * BN) + r * BN + c));
+			const T* b = reinterpret_cast<const T*>(&nxt);
+#pragma unroll
+			for (int e = 0; e < E; ++e)
+			{
+				a[e] = a[e] + b[e];
+			}
+		}
+		T* dst = C + (int64_t) m * c_rs + n;
+		if (vec_store && n + E <= N)
+		{
+			*reinterpret_cast<V*>(dst) = acc;
+		}
+		else
+		{
+#pragma unroll
+			for (int e = 0; e < E; ++e)
+			{
+				if (n + e < N)
+				{
+					dst[e] = a[e];
+				}
+			}
+		}
+	}
+}
+
 /// dst[c * dst_ld + r] = src[r * src_ld + c] through 32 x 32 (+1) smem tiles:
 /// both sides coalesced.  Used to hand the FMA kernels their fastest operand
 /// layout ([k][row], see relayout below).
@@ -255,7 +337,10 @@ int make_ready (llo_cuda_ctx* ctx, Scratch& scratch, const T*& base,
 /// the tensor maps, choose split-K, and call
 ///   launch(ak, bk, map_a, map_b, args, splits) -> status
 /// `vec_a` / `vec_b` give the C store vector width (elements) per B layout.
-template <typename T, int BM, int BN, int BK, typename Launch>
+/// PERSIST: the kernel is persistent (one CTA per SM walking work units,
+/// operand pipeline kept full across units) and takes the tail-split plan
+/// (full_tiles / tail_splits / part) instead of the (tile, split) grid.
+template <typename T, int BM, int BN, int BK, bool PERSIST = false, typename Launch>
 int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 	const T* B, bool& handled, int vec_nc, int vec_kc, Launch launch)
 {
@@ -354,12 +439,78 @@ int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 	{
 		return LLO_OK;
 	}
+	uint32_t ktiles = (uint32_t) ((p.K + BK - 1) / BK);
+	int64_t need = bk ? vec_kc : vec_nc;
+	if (PERSIST)
+	{
+		// Work units are handed round-robin to one CTA per SM.  Whole rounds
+		// of the grid run whole tiles; the tiles of the last, partial round
+		// may be cut along k into `splits` ranges (summed in range order by a
+		// second pass) when that shortens the round.  Cost model in k-tile
+		// times: rounds x (k-tiles per unit + ~2 for the epilogue and the
+		// pipeline bubble) + 2 for the fold pass.  With fewer tiles than SMs
+		// this is plain split-K.
+		uint64_t sms = (uint64_t) ctx->sm_count;
+		uint64_t rest = tiles % sms;
+		uint32_t splits = 1;
+		if (0 != rest)
+		{
+			uint64_t best = (uint64_t) ktiles + 2;
+			uint64_t most = std::min<uint64_t>(ktiles / 4, 64);
+			for (uint64_t cand = 2; cand <= most; ++cand)
+			{
+				uint64_t per = (ktiles + cand - 1) / cand;
+				uint64_t real = (ktiles + per - 1) / per;
+				uint64_t rounds = (rest * real + sms - 1) / sms;
+				uint64_t c = rounds * (per + 2) + 2;
+				if (c * 100 < best * 95) // worth it only for a clear gain
+				{
+					best = c;
+					splits = (uint32_t) real;
+				}
+			}
+		}
+		if (const char* forced = std::getenv("LLO_GEMM_SPLITS"))
+		{
+			// experiments only (tools/gemm_bench.py)
+			splits = (uint32_t) std::max(1, std::min(std::atoi(forced), (int) ktiles));
+		}
+		args.ktiles = ktiles;
+		args.kt_per_split = (ktiles + splits - 1) / splits;
+		splits = (ktiles + args.kt_per_split - 1) / args.kt_per_split;
+		args.tail_splits = splits;
+		args.full_tiles = splits > 1 ? (uint32_t) (tiles - rest) : (uint32_t) tiles;
+		args.part = nullptr;
+		args.split_stride = 0;
+		args.C = C;
+		args.c_rs = p.c_rs;
+		args.vec_store = (0 == ((uintptr_t) C & (uintptr_t) (need * sizeof(T) - 1)) &&
+			0 == p.c_rs % need) ? 1 : 0;
+		uint32_t tail_tiles = (uint32_t) tiles - args.full_tiles;
+		if (tail_tiles > 0)
+		{
+			void* ws = nullptr;
+			LLO_TRY(scratch.get(&ws, (size_t) tail_tiles * splits * BM * BN * sizeof(T)));
+			args.part = (T*) ws;
+		}
+		handled = true;
+		LLO_TRY(launch(ak, bk, ma, mb, args, splits));
+		if (tail_tiles > 0)
+		{
+			int64_t unit = (int64_t) (16 / sizeof(T));
+			uint32_t vec = (0 == ((uintptr_t) C & 15u) && 0 == p.c_rs % unit) ? 1 : 0;
+			tile_fold_kernel<T,BM,BN><<<dim3(tail_tiles, 8), 256, 0, ctx->stream>>>(
+				C, p.c_rs, args.part, (uint32_t) p.M, (uint32_t) p.N,
+				args.tiles_m, args.tiles_n, args.full_tiles, splits, vec);
+			LLO_TRY(launched(ctx, "tile_fold_kernel"));
+		}
+		return LLO_OK;
+	}
 	// split-K: the k-tiles of every output tile may be spread over `splits`
 	// CTAs (partial products summed in split order by a second pass) when
 	// that fills the SMs better.  Cost model in k-tile times: waves of CTAs
 	// x (k-tiles per CTA + ~3 for pipeline fill and epilogue), plus one for
 	// the fold pass.
-	uint32_t ktiles = (uint32_t) ((p.K + BK - 1) / BK);
 	uint32_t splits = 1;
 	{
 		uint64_t sms = (uint64_t) ctx->sm_count;
@@ -388,7 +539,6 @@ int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 	}
 	args.kt_per_split = (ktiles + splits - 1) / splits;
 	splits = (ktiles + args.kt_per_split - 1) / args.kt_per_split;
-	int64_t need = bk ? vec_kc : vec_nc;
 	T* part = nullptr;
 	int64_t part_ld = 0;
 	if (splits > 1)

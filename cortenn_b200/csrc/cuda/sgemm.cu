@@ -89,6 +89,415 @@ struct Frag
 
 template <bool AK, bool BKC>
 __global__ void __launch_bounds__(THREADS, 1)
+sgemm_persist_kernel (const __grid_constant__ CUtensorMap map_a,
+	const __grid_constant__ CUtensorMap map_b,
+	const __grid_constant__ SgemmArgs args)
+{
+	extern __shared__ __align__(1024) unsigned char smem_raw[];
+	// 128-byte swizzled tiles must start on a 1024-byte boundary
+	// (offset arithmetic on the __shared__ symbol keeps the address space,
+	// so tile reads compile to LDS rather than generic LD)
+	unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+	float* tiles_a = (float*) smem;
+	float* tiles_b = tiles_a + STAGES * A_STAGE_FLOATS;
+	uint64_t* full = (uint64_t*) (smem + (size_t) STAGES * STAGE_BYTES + TAIL_PAD);
+	uint64_t* empty = full + STAGES;
+
+	// Persistent: one CTA per SM walks work units.  Units [0, full_tiles)
+	// are whole tiles; the others are k ranges of the tail tiles (see
+	// GemmArgs).  The operand pipeline runs across unit boundaries: while a
+	// unit's last k-tiles are multiplied and its outputs stored, the TMA
+	// loads of the next unit are already in flight.
+	// Unit sequence of CTA c: c, c + grid, c + 2 grid, ...
+	const uint32_t grid = gridDim.x;
+	const uint32_t units = args.full_tiles +
+		(args.tiles_m * args.tiles_n - args.full_tiles) * args.tail_splits;
+	// k-tiles of unit u
+	auto unit_ktiles = [&] (uint32_t u) -> uint32_t
+	{
+		if (u < args.full_tiles)
+		{
+			return args.ktiles;
+		}
+		uint32_t split = (u - args.full_tiles) % args.tail_splits;
+		return min(args.ktiles - split * args.kt_per_split, args.kt_per_split);
+	};
+
+	int warp = threadIdx.x >> 5;
+	int lane = threadIdx.x & 31;
+
+	// one elected lane moves both operand tiles of k-tile `kt` of unit `u`
+	// into stage `s` with TMA
+	auto issue = [&] (uint32_t u, uint32_t kt, uint32_t s)
+	{
+		uint32_t tile = u, kt_begin = 0;
+		if (u >= args.full_tiles)
+		{
+			uint32_t t = u - args.full_tiles;
+			tile = args.full_tiles + t / args.tail_splits;
+			kt_begin = (t % args.tail_splits) * args.kt_per_split;
+		}
+		uint32_t tile_m, tile_n;
+		tile_coords(tile, args.tiles_m, args.tiles_n, tile_m, tile_n);
+		mbar_expect_tx(&full[s], STAGE_BYTES);
+		int k0 = (int) ((kt_begin + kt) * BK);
+		if (AK)
+		{
+			tma_load_2d(tiles_a + s * A_STAGE_FLOATS, &map_a, &full[s],
+				k0, (int) (tile_m * BM));
+		}
+		else
+		{
+			tma_load_2d(tiles_a + s * A_STAGE_FLOATS, &map_a, &full[s],
+				(int) (tile_m * BM), k0);
+		}
+		if (BKC)
+		{
+			tma_load_2d(tiles_b + s * B_STAGE_FLOATS, &map_b, &full[s],
+				k0, (int) (tile_n * BN));
+		}
+		else
+		{
+			tma_load_2d(tiles_b + s * B_STAGE_FLOATS, &map_b, &full[s],
+				(int) (tile_n * BN), k0);
+		}
+	};
+
+	// producer cursor (the k-tile LEAD items ahead of the consumer), tracked
+	// by every thread because the duty rotates
+	uint32_t c_unit = blockIdx.x;   // the unit being multiplied
+	uint32_t p_unit = blockIdx.x;
+	uint32_t p_kt = 0;
+	uint32_t p_cnt = p_unit < units ? unit_ktiles(p_unit) : 0;
+	auto p_advance = [&] ()
+	{
+		if (++p_kt == p_cnt)
+		{
+			p_unit += grid;
+			p_kt = 0;
+			p_cnt = p_unit < units ? unit_ktiles(p_unit) : 0;
+		}
+	};
+
+	if (0 == threadIdx.x)
+	{
+		for (int s = 0; s < STAGES; ++s)
+		{
+			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], WARPS);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
+		asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b) : "memory");
+	}
+	for (uint32_t g = 0; g < LEAD; ++g)
+	{
+		if (p_unit < units)
+		{
+			if (0 == threadIdx.x)
+			{
+				issue(p_unit, p_kt, g);
+			}
+			p_advance();
+		}
+	}
+	__syncthreads();
+
+	int wm = warp >> 2;   // 0..1
+	int wn = warp & 3;    // 0..3
+	int tm = lane >> 2;   // 0..7
+	int tn = lane & 3;    // 0..3
+	float acc[8][8];
+#pragma unroll
+	for (int i = 0; i < 8; ++i)
+	{
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+		{
+			acc[i][j] = 0.0f;
+		}
+	}
+
+	// thread-constant parts of the fragment addresses (in float4 units)
+	//   KC : row * 8 + (kg ^ (row & 7)), rows r0 + 8i resp. cols c(j)
+	//   else: k * 32 + row / 4
+	const int a_row4 = AK ? (wm * 64 + tm) * (BK / 4) : (wm * 64 + tm * 4) / 4;
+	const int b_row4 = BKC ? 0 : (wn * 32 + tn * 4) / 4;
+	const int a_key = tm;
+	int b_col[8];
+	if (BKC)
+	{
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+		{
+			b_col[j] = wn * 32 + col_of<true>(tn, j);
+		}
+	}
+
+	uint32_t c_kt = 0;
+	uint32_t c_cnt = c_unit < units ? unit_ktiles(c_unit) : 0;
+	for (uint32_t g = 0; c_unit < units; ++g)
+	{
+		uint32_t s = g % STAGES;
+		// the producer duty rotates over the warps: item g + LEAD goes into
+		// the stage every warp released STAGES - LEAD iterations ago
+		if (p_unit < units)
+		{
+			if ((int) (g % WARPS) == warp && 0 == lane)
+			{
+				uint32_t pg = g + LEAD;
+				if (pg >= STAGES)
+				{
+					uint32_t prev = pg - STAGES;
+					mbar_wait(&empty[prev % STAGES], (prev / STAGES) & 1);
+				}
+				issue(p_unit, p_kt, pg % STAGES);
+			}
+			p_advance();
+		}
+		__syncwarp();
+		mbar_wait(&full[s], (g / STAGES) & 1);
+		const float4* As4 = (const float4*) (tiles_a + s * A_STAGE_FLOATS);
+		const float4* Bs4 = (const float4*) (tiles_b + s * B_STAGE_FLOATS);
+
+		Frag<AK> fa;
+		Frag<BKC> fb;
+		// ---- prologue: fragments of k-group 0 / k 0 ----
+		if (AK)
+		{
+#pragma unroll
+			for (int i = 0; i < 8; ++i)
+			{
+				fa.v[0][i] = As4[a_row4 + i * 8 * (BK / 4) + (0 ^ a_key)];
+			}
+		}
+		else
+		{
+			fa.v[0][0] = As4[a_row4];
+			fa.v[0][1] = As4[a_row4 + 8];
+		}
+		if (BKC)
+		{
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+			{
+				fb.v[0][j] = Bs4[b_col[j] * (BK / 4) + (0 ^ (b_col[j] & 7))];
+			}
+		}
+		else
+		{
+			fb.v[0][0] = Bs4[b_row4];
+			fb.v[0][1] = Bs4[b_row4 + 4];
+		}
+
+#pragma unroll 1
+		for (int kgp = 0; kgp < BK / 8; ++kgp)
+		{
+#pragma unroll
+			for (int h = 0; h < 2; ++h)
+			{
+				const int kg = 2 * kgp + h;
+				// (the prefetch of the last step reads past the stage: unused)
+				const bool more_kg = true;
+#pragma unroll
+				for (int kk = 0; kk < 4; ++kk)
+				{
+					const int k = kg * 4 + kk;
+					const bool more_k = (kk < 3) || more_kg;
+					// ---- prefetch ----
+					if (AK)
+					{
+						if (more_kg)
+						{
+							int chunk = (kg + 1) ^ a_key;
+							fa.v[h ^ 1][2 * kk] = As4[a_row4 +
+								(2 * kk) * 8 * (BK / 4) + chunk];
+							fa.v[h ^ 1][2 * kk + 1] = As4[a_row4 +
+								(2 * kk + 1) * 8 * (BK / 4) + chunk];
+						}
+					}
+					else if (more_k)
+					{
+						fa.v[(kk + 1) & 1][0] = As4[(k + 1) * (BM / 4) + a_row4];
+						fa.v[(kk + 1) & 1][1] = As4[(k + 1) * (BM / 4) + a_row4 + 8];
+					}
+					if (BKC)
+					{
+						if (more_kg)
+						{
+#pragma unroll
+							for (int q = 0; q < 2; ++q)
+							{
+								int j = 2 * kk + q;
+								fb.v[h ^ 1][j] = Bs4[b_col[j] * (BK / 4) +
+									((kg + 1) ^ (b_col[j] & 7))];
+							}
+						}
+					}
+					else if (more_k)
+					{
+						fb.v[(kk + 1) & 1][0] = Bs4[(k + 1) * (BN / 4) + b_row4];
+						fb.v[(kk + 1) & 1][1] = Bs4[(k + 1) * (BN / 4) + b_row4 + 4];
+					}
+					// ---- this k ----
+					float a[8];
+					float b[8];
+					if (AK)
+					{
+#pragma unroll
+						for (int i = 0; i < 8; ++i)
+						{
+							a[i] = comp(fa.v[h][i], kk);
+						}
+					}
+					else
+					{
+						float4 lo = fa.v[kk & 1][0];
+						float4 hi = fa.v[kk & 1][1];
+						a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w;
+						a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+					}
+					if (BKC)
+					{
+#pragma unroll
+						for (int j = 0; j < 8; ++j)
+						{
+							b[j] = comp(fb.v[h][j], kk);
+						}
+					}
+					else
+					{
+						float4 lo = fb.v[kk & 1][0];
+						float4 hi = fb.v[kk & 1][1];
+						b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = lo.w;
+						b[4] = hi.x; b[5] = hi.y; b[6] = hi.z; b[7] = hi.w;
+					}
+#pragma unroll
+					for (int i = 0; i < 8; ++i)
+					{
+#pragma unroll
+						for (int j = 0; j < 8; ++j)
+						{
+							acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+						}
+					}
+				}
+			}
+		}
+		__syncwarp();
+		if (0 == lane)
+		{
+			mbar_arrive(&empty[s]);
+		}
+		if (++c_kt < c_cnt)
+		{
+			continue;
+		}
+
+		// ---- the unit is complete: registers -> C (or its partial tile) ----
+		if (c_unit >= args.full_tiles)
+		{
+			// partial product of a tail tile: dense [BM][BN], always in range
+			float* ptile = args.part + (size_t) (c_unit - args.full_tiles) * (BM * BN) +
+				(wm * 64) * BN + wn * 32;
+#pragma unroll
+			for (int i = 0; i < 8; ++i)
+			{
+				float* prow = ptile + row_of<AK>(tm, i) * BN;
+				if (BKC)
+				{
+#pragma unroll
+					for (int j = 0; j < 8; j += 2)
+					{
+						*(float2*) (prow + col_of<true>(tn, j)) =
+							make_float2(acc[i][j], acc[i][j + 1]);
+					}
+				}
+				else
+				{
+#pragma unroll
+					for (int j = 0; j < 8; j += 4)
+					{
+						*(float4*) (prow + col_of<false>(tn, j)) = make_float4(
+							acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+					}
+				}
+			}
+		}
+		else
+		{
+			uint32_t tile_m, tile_n;
+			tile_coords(c_unit, args.tiles_m, args.tiles_n, tile_m, tile_n);
+			uint32_t m_base = tile_m * BM + wm * 64;
+			uint32_t n_base = tile_n * BN + wn * 32;
+#pragma unroll
+			for (int i = 0; i < 8; ++i)
+			{
+				uint32_t m = m_base + row_of<AK>(tm, i);
+				if (m >= args.M)
+				{
+					continue;
+				}
+				float* crow = args.C + (int64_t) m * args.c_rs;
+				if (BKC)
+				{
+#pragma unroll
+					for (int j = 0; j < 8; j += 2)
+					{
+						uint32_t n = n_base + col_of<true>(tn, j);
+						if (args.vec_store && n + 1 < args.N)
+						{
+							*(float2*) (crow + n) = make_float2(acc[i][j], acc[i][j + 1]);
+						}
+						else
+						{
+							if (n < args.N) { crow[n] = acc[i][j]; }
+							if (n + 1 < args.N) { crow[n + 1] = acc[i][j + 1]; }
+						}
+					}
+				}
+				else
+				{
+#pragma unroll
+					for (int j = 0; j < 8; j += 4)
+					{
+						uint32_t n = n_base + col_of<false>(tn, j);
+						if (args.vec_store && n + 3 < args.N)
+						{
+							*(float4*) (crow + n) = make_float4(acc[i][j], acc[i][j + 1],
+								acc[i][j + 2], acc[i][j + 3]);
+						}
+						else
+						{
+#pragma unroll
+							for (int e = 0; e < 4; ++e)
+							{
+								if (n + e < args.N) { crow[n + e] = acc[i][j + e]; }
+							}
+						}
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < 8; ++i)
+		{
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+			{
+				acc[i][j] = 0.0f;
+			}
+		}
+		c_unit += grid;
+		c_kt = 0;
+		c_cnt = c_unit < units ? unit_ktiles(c_unit) : 0;
+	}
+}
+
+// ---- one CTA per (tile, split): the hardware hands tiles to SMs -----------------
+
+template <bool AK, bool BKC>
+__global__ void __launch_bounds__(THREADS, 1)
 sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 	const __grid_constant__ CUtensorMap map_b,
 	const __grid_constant__ SgemmArgs args)
@@ -401,6 +810,21 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 // ---- host side -----------------------------------------------------------------
 
 template <bool AK, bool BKC>
+int launch_persist (llo_cuda_ctx* ctx, const CUtensorMap& ma,
+	const CUtensorMap& mb, const SgemmArgs& args, uint32_t splits)
+{
+	LLO_CUDA_TRY(cudaFuncSetAttribute(sgemm_persist_kernel<AK,BKC>,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM_BYTES));
+	(void) splits;
+	uint64_t units = (uint64_t) args.full_tiles +
+		((uint64_t) args.tiles_m * args.tiles_n - args.full_tiles) * args.tail_splits;
+	unsigned grid = (unsigned) std::min<uint64_t>(units, (uint64_t) ctx->sm_count);
+	sgemm_persist_kernel<AK,BKC><<<grid, THREADS, SMEM_BYTES,
+		ctx->stream>>>(ma, mb, args);
+	return launched(ctx, "sgemm_persist_kernel");
+}
+
+template <bool AK, bool BKC>
 int launch_variant (llo_cuda_ctx* ctx, const CUtensorMap& ma,
 	const CUtensorMap& mb, const SgemmArgs& args, uint32_t splits)
 {
@@ -427,7 +851,39 @@ int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p, float* C,
 		}
 		// shapes the tensor-core kernel declines run exactly
 	}
-	return tma::drive<float,BM,BN,BK>(ctx, p, C, A, B, handled, 4, 2,
+	// The persistent kernel keeps the operand pipeline full across tiles and
+	// splits only the last partial round of the grid: it wins when tiles are
+	// short (few k-tiles, so the per-tile fill / drain of the tile-grid kernel
+	// weighs 10-15%) and there is at least one full round; long-k problems run
+	// ~4% faster on the tile grid (measured A/B on one box: 8192x1024x784
+	// 40.7 -> 44.0, 8192x1024x1024 41.2 -> 45.6, 8192^3 54.8 -> 52.6 TFLOP/s).
+	bool persist = false;
+	{
+		uint64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+		uint64_t tiles_t = ((p.N + BM - 1) / BM) * ((p.M + BN - 1) / BN);
+		uint64_t ktiles = (p.K + BK - 1) / BK;
+		persist = std::min(tiles, tiles_t) >= (uint64_t) ctx->sm_count && ktiles <= 64;
+	}
+	if (const char* env = std::getenv("LLO_GEMM_PERSIST"))
+	{
+		persist = 0 != std::atoi(env); // experiments (tools/gemm_bench.py)
+	}
+	if (persist)
+	{
+		return tma::drive<float,BM,BN,BK,true>(ctx, p, C, A, B, handled, 4, 2,
+			[ctx] (bool ak, bool bk, const CUtensorMap& ma, const CUtensorMap& mb,
+				const SgemmArgs& args, uint32_t splits) -> int
+			{
+				if (ak)
+				{
+					return bk ? launch_persist<true,true>(ctx, ma, mb, args, splits) :
+						launch_persist<true,false>(ctx, ma, mb, args, splits);
+				}
+				return bk ? launch_persist<false,true>(ctx, ma, mb, args, splits) :
+					launch_persist<false,false>(ctx, ma, mb, args, splits);
+			});
+	}
+	return tma::drive<float,BM,BN,BK,false>(ctx, p, C, A, B, handled, 4, 2,
 		[ctx] (bool ak, bool bk, const CUtensorMap& ma, const CUtensorMap& mb,
 			const SgemmArgs& args, uint32_t splits) -> int
 		{
