@@ -13,6 +13,11 @@
 ///   "simplify"    1 = allow x*1 -> x and (x*y)/x -> y in derived graphs
 ///                 (the second is inexact by <= 1 ulp and defined at x == 0,
 ///                 where the reference yields NaN)
+///   "recompute"   n > 0 = an elementwise producer with several consumers is
+///                 recomputed inside each of them when its fully inlined
+///                 program has at most n instructions (and 2 inputs) instead
+///                 of being stored and read back; 0 = every shared producer
+///                 is materialised once
 ///   "tf32x3"      1 = opt-in 3xTF32 tensor-core GEMM for fp32
 ///   "sequential_reduce" 1 = reference summation order for reductions
 ///

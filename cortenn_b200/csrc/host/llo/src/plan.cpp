@@ -1,5 +1,9 @@
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <string>
 #include <unordered_map>
 
 #include "llo/plan.hpp"
@@ -340,7 +344,8 @@ static bool is_unsigned (DT t)
 
 struct Plan
 {
-	Plan (DT dtype) : dtype_(dtype), simplify_(0 != get_option("simplify")) {}
+	Plan (DT dtype) : dtype_(dtype), simplify_(0 != get_option("simplify")),
+		recompute_((int) get_option("recompute")) {}
 
 	PNode* make (Kind kind)
 	{
@@ -673,9 +678,61 @@ struct Plan
 		return a.node_ == b.node_ && a.view_ == b.view_;
 	}
 
+	/// op over constant arguments in the arithmetic of T, argument order as
+	/// the device applies it (only operations IEEE defines exactly)
+	template <typename T>
+	static bool fold_consts (double& out, int op, const std::vector<PArg>& args)
+	{
+		T acc = (T) args[0].node_->value_;
+		if (age::NEG == op) { out = (double) (T) -acc; return true; }
+		if (age::ABS == op) { out = (double) (T) std::fabs(acc); return true; }
+		for (size_t i = 1; i < args.size(); ++i)
+		{
+			T x = (T) args[i].node_->value_;
+			switch (op)
+			{
+				case age::SUM: acc = acc + x; break;
+				case age::PROD: acc = acc * x; break;
+				case age::SUB: acc = acc - x; break;
+				case age::DIV: acc = acc / x; break;
+				default: return false;
+			}
+		}
+		if (args.size() < 2)
+		{
+			return false;
+		}
+		out = (double) acc;
+		return true;
+	}
+
 	PNode* make_elem (int op, const ade::Shape& shape, std::vector<PArg> args,
 		DT dtype)
 	{
+		// constant sub-expressions (the derivative rules build -1 as neg(1),
+		// 2 - 1, 1 / batch, ...) never reach the device
+		if ((age::FLOAT == dtype || age::DOUBLE == dtype) && false == args.empty())
+		{
+			bool all_const = true;
+			for (const PArg& a : args)
+			{
+				all_const = all_const && Kind::CONST == a.node_->kind_;
+			}
+			double value = 0;
+			if (all_const && (age::FLOAT == dtype ?
+				fold_consts<float>(value, op, args) :
+				fold_consts<double>(value, op, args)))
+			{
+				++stats_.simplified_;
+				return make_const(value, shape, dtype);
+			}
+		}
+		if (simplify_ && age::POW == op && 2 == args.size() && is_const(args[1], 1))
+		{
+			// pow(x, 1) -> x (exact)
+			++stats_.simplified_;
+			return make_view(shape, args[0], dtype);
+		}
 		if (simplify_)
 		{
 			if (age::PROD == op || age::SUM == op)
@@ -773,10 +830,26 @@ struct Plan
 		}
 	}
 
-	bool inlinable (const PNode* n) const
+	/// A producer is emitted inside its consumer's program when nothing else
+	/// needs its value -- or ("recompute" option) when its fully inlined form
+	/// is so short that recomputing it in every consumer costs less than a
+	/// pass over HBM to store it and one per consumer to read it back
+	bool inlinable (PNode* n)
 	{
-		return Kind::ELEM == n->kind_ && 1 == n->uses_ &&
-			nullptr == n->data_ && false == n->has_rand_;
+		if (Kind::ELEM != n->kind_ || nullptr != n->data_ || n->has_rand_)
+		{
+			return false;
+		}
+		if (1 == n->uses_)
+		{
+			return true;
+		}
+		if (recompute_ <= 0)
+		{
+			return false;
+		}
+		measure(n);
+		return n->need_insns_ <= recompute_ && n->need_inputs_ <= 2;
 	}
 
 	/// Size of node n's program when every inlinable producer is inlined
@@ -960,8 +1033,41 @@ struct Plan
 		}
 	}
 
+	/// LLO_PLAN_TRACE=1: one line per device step on stderr
+	static bool tracing (void)
+	{
+		static const bool on = nullptr != std::getenv("LLO_PLAN_TRACE");
+		return on;
+	}
+
+	void trace_program (const Program& prog, const PNode* n) const
+	{
+		std::string text = "program " + n->shape_.to_string() + " in=" +
+			std::to_string(prog.inputs_.size()) + " :";
+		for (const llo_cuda_insn& insn : prog.code_)
+		{
+			if (LLO_VM_LOAD == insn.op)
+			{
+				text += " L" + std::to_string((int) insn.arg);
+			}
+			else if (LLO_VM_CONST == insn.op)
+			{
+				text += " C(" + std::to_string(prog.consts_[insn.arg]) + ")";
+			}
+			else
+			{
+				text += " " + age::name_op((age::_GENERATED_OPCODE) insn.op);
+			}
+		}
+		std::fprintf(stderr, "[plan] %s\n", text.c_str());
+	}
+
 	void run_program (Program& prog, PNode* n)
 	{
+		if (tracing())
+		{
+			trace_program(prog, n);
+		}
 		n->data_ = device::alloc(n->shape_.n_elems() * age::type_size(n->dtype_));
 		uint64_t outshape[R];
 		std::copy(n->shape_.begin(), n->shape_.end(), outshape);
@@ -1055,7 +1161,17 @@ struct Plan
 	{
 		if (age::SUM == n->opcode_ && try_gemm(n))
 		{
+			if (tracing())
+			{
+				std::fprintf(stderr, "[plan] gemm -> %s\n", n->shape_.to_string().c_str());
+			}
 			return;
+		}
+		if (tracing())
+		{
+			std::fprintf(stderr, "[plan] reduce %s %s -> %s\n",
+				age::name_op((age::_GENERATED_OPCODE) n->opcode_).c_str(),
+				n->argshape_.to_string().c_str(), n->shape_.to_string().c_str());
 		}
 		PArg& src = n->args_[0];
 		std::shared_ptr<char> data;
@@ -1235,6 +1351,7 @@ struct Plan
 
 	DT dtype_;
 	bool simplify_;
+	int recompute_;
 	PlanStats stats_;
 	std::vector<std::unique_ptr<PNode>> arena_;
 	std::map<std::pair<ade::iTensor*,int>,PNode*> memo_;
