@@ -204,6 +204,28 @@ def test_shared_subgraphs_are_evaluated_once():
     assert llo.launch_count() - before == 2
 
 
+def test_constant_subexpressions_fold_on_the_host():
+    """neg(1), 2 - 1, 1 / n of the derivative rules become immediates: no
+    launch fills a tensor with a constant, results unchanged"""
+    rng = np.random.default_rng(29)
+    data = rng.uniform(0.5, 2, (48, 40)).astype(F4)
+    x = llo.variable(data, "x")
+    shape = [48, 40]
+    minus_one = age.neg(llo.scalar(1.0, shape))
+    inv_n = age.div(llo.scalar(1.0, shape), llo.scalar(8.0, shape))
+    expo = age.sub(llo.scalar(2.0, shape), llo.scalar(1.0, shape))
+    root = age.mul(age.mul(age.pow(x, expo), minus_one), inv_n)
+    llo.set_option("plan", 1)
+    before = llo.launch_count()
+    got = check(root, F4, what="folded constants")
+    assert llo.launch_count() - before == 1
+    assert llo.plan_stats()["programs"] == 1
+    np.testing.assert_array_equal(got, -data / np.float32(8.0))   # pow(x, 1) = x, * -1, * 0.125: exact
+    # a graph that is constant altogether still evaluates (materialised once)
+    check(age.add(minus_one, inv_n), F4, what="constant root")
+    check(age.add(minus_one, inv_n), F8, what="constant root f64")
+
+
 def test_random_expression_graphs(mode):
     rng = np.random.default_rng(19)
     unary = [age.abs, age.neg, age.sin, age.cos, age.exp, age.sqrt, age.round, age.log]
@@ -288,7 +310,8 @@ def test_tf32x3_option_routes_matmul_to_the_tensor_cores():
     assert (np.abs(ref - fast) <= 1e-6 * scale).all()
 
 
-@pytest.mark.parametrize("side,extra", [(200, ()), (256, ()), (130, (3,)), (64, ()), (65, (2,))])
+@pytest.mark.parametrize("side,extra", [(200, ()), (256, ()), (130, (3,)), (64, ()), (65, (2,)), (192, (2,)),
+                                        (320, (2, 2))])
 def test_program_with_a_tensor_and_its_transpose(side, extra):
     """f(x, permute(x)): the tile engine computes output tiles (i,j) and (j,i)
     from the two input tiles it staged once (vm_pair4_kernel); ragged sizes,

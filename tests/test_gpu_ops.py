@@ -355,6 +355,42 @@ def test_gemm(ctx, dtype, layout):
         assert (np.abs(expect - got) <= tol * scale).all()
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("layout", ["nn", "nt", "tn", "tt"])
+@pytest.mark.parametrize("mnk", [
+    (2048, 1280, 96),     # 160 short tiles: the persistent kernel, tail tiles split along k
+    (2000, 1300, 100),    # the same, ragged edges
+    (2432, 2432, 40),     # 361 tiles: two full rounds + a split tail
+    (128, 256, 4096),     # two tiles, long k: split-K with the fixed-order fold
+    (1000, 10, 3000),     # skinny output (re-pitched operand)
+])
+def test_gemm_schedules(ctx, dtype, layout, mnk):
+    """every work decomposition of the TMA GEMMs (tile grid, split-K, persistent
+    with a split tail) against a float64 product"""
+    rng = np.random.default_rng(47)
+    M, N, K = mnk
+    A = rng.uniform(-1, 1, (M, K)).astype(dtype)
+    B = rng.uniform(-1, 1, (K, N)).astype(dtype)
+    a_store = A if layout[0] == "n" else np.ascontiguousarray(A.T)
+    b_store = B if layout[1] == "n" else np.ascontiguousarray(B.T)
+    a_rs, a_cs = (K, 1) if layout[0] == "n" else (1, M)
+    b_rs, b_cs = (N, 1) if layout[1] == "n" else (1, K)
+    pa = ctx.upload(a_store); pb = ctx.upload(b_store)
+    pc = ctx.alloc(M * N * np.dtype(dtype).itemsize)
+    got = []
+    for _ in range(2):
+        capi.check(ctx.lib.llo_cuda_gemm(ctx.handle, capi.dtype_code(dtype), M, N, K,
+                                         pa, a_rs, a_cs, pb, b_rs, b_cs, pc, N, 1, 0))
+        got.append(ctx.download(pc, M * N, dtype).reshape(M, N))
+    for p in (pa, pb, pc):
+        ctx.free(p)
+    expect = A.astype(np.float64) @ B.astype(np.float64)
+    tol = 1e-6 if dtype == np.float32 else 1e-12
+    scale = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64)
+    assert (np.abs(expect - got[0]) <= tol * scale).all()
+    np.testing.assert_array_equal(got[0], got[1])   # fixed summation order: run-to-run identical
+
+
 @pytest.mark.parametrize("layout", ["nn", "nt", "tn", "tt"])
 @pytest.mark.parametrize("mnk", [(256, 384, 512), (300, 200, 1000), (129, 131, 2085)])
 def test_gemm_3xtf32_tensor_core_path(ctx, layout, mnk):
