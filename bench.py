@@ -154,6 +154,33 @@ def cpu_chain(side, repeats):
     return sec, workloads.chain_bytes(side) / sec / 1e9
 
 
+def cpu_config1(age, llo):
+    """BASELINE.json configs[0]: the reference's CPU-runnable unit graphs over float
+    [64,64] through the oracle (single thread): ns per output element, median of 10"""
+    oracle = oracle_module()
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0.5, 1.5, (64, 64)).astype(np.float32)
+    y = rng.uniform(0.5, 1.5, (64, 64)).astype(np.float32)
+    vx, vy = llo.variable(x, "x"), llo.variable(y, "y")
+    graphs = {"add": age.add(vx, vy), "mul": age.mul(vx, vy), "exp": age.exp(vx),
+              "reduce_sum_dim1": age.reduce_sum(vx, 1), "reduce_sum_all": age.reduce_sum0(vx),
+              "matmul": age.matmul(vx, vy)}
+    out = {}
+    for name, root in graphs.items():
+        times = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            oracle.evaluate(root, F32)
+            times.append(time.perf_counter() - t0)
+        sec = float(np.median(times))
+        entry = {"us": sec * 1e6, "ns_per_input_elem": sec * 1e9 / 4096}
+        if name == "matmul":
+            entry["MFLOPs"] = 2.0 * 64 ** 3 / sec / 1e6
+        out[name] = entry
+    out["note"] = "oracle = CPU restatement of llo::Evaluator, 1 thread, ade shape [64,64] fp32"
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -253,7 +280,53 @@ def side_workloads(args, timer, age, llo, rank, world):
             gbps = nbytes / ms / 1e6
             out[name] = {"GBps": gbps, "ms": ms, "frac_of_measured_hbm": gbps / hbm_peak,
                          "launches_per_eval": launches // steps}
-        del vx, x, cases
+        del cases
+        # config 3, reference-representable shape: [128,128,128,128], reduce_*(x, 2)
+        x4 = x.reshape(128, 128, side * side // (128 * 128 * 128), 128) if side * side >= 128 ** 4 else None
+        if x4 is not None:
+            vx4 = llo.variable(x4, "x4")
+            for name, root in (("reduce_sum_128x4_dim2", age.reduce_sum(vx4, 2)),
+                               ("reduce_max_128x4_dim2", age.reduce_max(vx4, 2))):
+                ms, launches = timer.timed(lambda r=root: llo.evaluate_device(r, F32), steps, warm)
+                gbps = nbytes / ms / 1e6
+                out[name] = {"GBps": gbps, "ms": ms, "frac_of_measured_hbm": gbps / hbm_peak,
+                             "launches_per_eval": launches // steps}
+            del vx4
+        # config 2, every operator stand-alone: algorithmic bytes =
+        # 4 * (distinct input elements + output elements)
+        y = np.random.default_rng(5).uniform(0.5, 2.0, (side, side)).astype(np.float32)
+        bb = np.random.default_rng(3).uniform(0.5, 2.0, (side,)).astype(np.float32)
+        vy, vbb = llo.variable(y, "y"), llo.variable(bb, "b")
+        n = side * side
+        ops = {
+            "exp": (age.exp(vx), 2 * n), "sin": (age.sin(vx), 2 * n), "sqrt": (age.sqrt(vx), 2 * n),
+            "abs": (age.abs(vx), 2 * n), "neg": (age.neg(vx), 2 * n), "log": (age.log(vx), 2 * n),
+            "add": (age.add(vx, vy), 3 * n), "sub": (age.sub(vx, vy), 3 * n),
+            "mul": (age.mul(vx, vy), 3 * n), "div": (age.div(vx, vy), 3 * n),
+            "pow": (age.pow(vx, vy), 3 * n), "lt": (age.lt(vx, vy), 3 * n), "eq": (age.eq(vx, vy), 3 * n),
+            "extend": (age.extend(vbb, 1, [side]), n + side),
+            "mul_extend": (age.mul(vx, age.extend(vbb, 1, [side])), 2 * n + side),
+            "permute": (age.permute(vx, [1, 0]), 2 * n),
+        }
+        elem = {}
+        for name, (root, elems) in ops.items():
+            ms, launches = timer.timed(lambda r=root: llo.evaluate_device(r, F32), steps, warm)
+            gbps = 4.0 * elems / ms / 1e6
+            elem[name] = {"GBps": round(gbps, 1), "ms": round(ms, 4), "frac_of_measured_hbm": round(gbps / hbm_peak, 3)}
+        out["elementwise_ops"] = elem
+        del ops, vy, vbb, y
+        # config 2, reference-representable shape: the chain over [128,128,128,128]
+        if x4 is not None:
+            vx4 = llo.variable(x4, "x4")
+            b4 = llo.variable(bb[:128].copy(), "b4")
+            rest = list(x4.shape[:-1])[::-1]
+            root = age.add(age.mul(age.exp(vx4), age.extend(b4, 1, rest)), age.permute(vx4, [1, 0, 2, 3]))
+            ms, launches = timer.timed(lambda: llo.evaluate_device(root, F32), steps, warm)
+            gbps = 4.0 * (2 * n + 128) / ms / 1e6
+            out["chain_128x4"] = {"GBps": gbps, "ms": ms, "frac_of_measured_hbm": gbps / hbm_peak,
+                                  "launches_per_eval": launches // steps}
+            del vx4, b4, root
+        del vx, x, x4, bb
         # config 4: matmul 8192^3 — fp32 on the FFMA pipe (exact path), fp64 on
         # the DFMA pipe, and the opt-in 3xTF32 tensor-core path (tcgen05)
         m = args.matmul
@@ -406,6 +479,8 @@ def run_own(args, rank, local_rank, world):
 
     del vx, vb, root, x, b
     side_results = side_workloads(args, timer, age, llo, rank, world)
+    if cpu_baseline is not None:
+        side_results["cpu_config1"] = cpu_config1(age, llo)
 
     if rank == 0:
         line = {

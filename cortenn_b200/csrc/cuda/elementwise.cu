@@ -636,7 +636,9 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 	T* spill = tiles + 4 * SLOT;
 	const uint32_t side = p.tiles0;
 	const uint32_t pairs = side * (side - 1) / 2;
-	const uint32_t per = pairs + side;       // work units per slice of the other dims
+	// work units per slice of the other dims: the off-diagonal pairs, then the
+	// diagonal tiles two at a time (every unit stages and computes two tiles)
+	const uint32_t per = pairs + (side + 1) / 2;
 	const uint32_t total = p.total_tiles;    // per * (product of the other dims)
 	const Tile4Thread th = tile4_thread();
 
@@ -653,7 +655,8 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 	const uint32_t dst_even = r0 * (VM_TS * 4) + ((pc ^ (r0 >> 2)) << 4);
 	const uint32_t dst_odd = dst_even ^ 64u;
 
-	// unit -> (i, j, brest); i == j on the diagonal
+	// unit -> (i, j, brest): i < j names the pair {(i,j), (j,i)}; i > j the
+	// diagonal tiles (j,j) and (i,i) = (j+1,j+1); i == j one diagonal tile
 	auto unit_of = [&] (uint32_t unit, uint32_t& i, uint32_t& j, uint32_t& brest)
 	{
 		brest = unit / per;
@@ -668,7 +671,8 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 		}
 		else
 		{
-			i = j = q - pairs;
+			j = 2 * (q - pairs);
+			i = j + 1 < side ? j + 1 : j;
 		}
 	};
 	// input tile of output tile (ti, tj) -> the slot at shared address `slot`
@@ -683,15 +687,24 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 				j * (16 * VM_TS * 4), src + j * rstep);
 		}
 	};
-	// slot 0 <- input tile of output (i,j), slot 1 <- input tile of output (j,i)
+	// pair: slot 0 <- input tile of output (i,j), slot 1 <- that of (j,i);
+	// diagonal: slot 0 <- tile (j,j), slot 1 <- tile (i,i)
 	auto stage_pair = [&] (int buf, uint32_t i, uint32_t j, uint32_t brest)
 	{
 		int32_t rest = rest_offset32(p, tin.stride, brest);
 		uint32_t slot = smem0 + (uint32_t) buf * (2 * SLOT * 4);
-		stage_one(slot, i, j, rest);
-		if (i != j)
+		if (i < j)
 		{
+			stage_one(slot, i, j, rest);
 			stage_one(slot + SLOT * 4, j, i, rest);
+		}
+		else
+		{
+			stage_one(slot, j, j, rest);
+			if (i != j)
+			{
+				stage_one(slot + SLOT * 4, i, i, rest);
+			}
 		}
 	};
 
@@ -722,16 +735,19 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 		}
 		__syncthreads();
 		T* slot0 = tiles + buf * 2 * SLOT;
-		T* slot1 = (i == j) ? slot0 : slot0 + SLOT;
+		T* slot1 = slot0 + SLOT;
 		int halves = (i == j) ? 1 : 2;
 #pragma unroll 1
 		for (int h = 0; h < halves; ++h)
 		{
-			// h = 0: output (i,j) from slot 0 transposed + slot 1 straight;
-			// h = 1: output (j,i) with the slots' roles swapped
-			run_tile<T,true>(p, th, h ? slot1 : slot0, spill,
-				(h ? j : i) * VM_TS, (h ? i : j) * VM_TS, brest,
-				h ? slot0 : slot1);
+			// pair (i < j): output (i,j) reads slot 0 transposed and slot 1
+			// straight, output (j,i) the other way round; diagonal tiles read
+			// their own slot both ways
+			const T* self = h ? slot1 : slot0;
+			const T* other = (i < j) ? (h ? slot0 : slot1) : self;
+			uint32_t t0 = (i < j) ? (h ? j : i) : (h ? i : j);
+			uint32_t t1 = (i < j) ? (h ? i : j) : t0;
+			run_tile<T,true>(p, th, self, spill, t0 * VM_TS, t1 * VM_TS, brest, other);
 		}
 		__syncthreads(); // everyone is done with this buffer
 		buf ^= 1;
@@ -1284,7 +1300,7 @@ static int launch_tile (llo_cuda_ctx* ctx, VmParams& p, int nstaged,
 			// work units: tile pairs + diagonal tiles, per slice of the other dims
 			uint64_t side = p.tiles0;
 			uint64_t units = (uint64_t) p.total_tiles / (side * side) *
-				(side * (side - 1) / 2 + side);
+				(side * (side - 1) / 2 + (side + 1) / 2);
 			p.total_tiles = (uint32_t) units;
 			size_t psmem = (size_t) 4 * VM_TS * VM_TS * sizeof(T) + spill;
 			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_pair4_kernel<T>,

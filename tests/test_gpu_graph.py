@@ -109,6 +109,19 @@ def test_matmul_lowers_to_gemm(dtype, mnk):
             assert (np.abs(want.astype(np.float64) - got) <= 4 * tol_of(dtype) * scale).all()
 
 
+def test_matmul_int32_1024_cubed_is_bit_exact():
+    """int32 randint(-8, 9) at 1024^3 (the sizes of
+    test_api.cpp:829-878 scaled up); every sum stays below 2^17, so a float64
+    BLAS product is the exact integer answer"""
+    rng = np.random.default_rng(8)
+    a = rng.integers(-8, 9, (1024, 1024)).astype(I4)
+    b = rng.integers(-8, 9, (1024, 1024)).astype(I4)
+    root = age.matmul(llo.variable(a, "a"), llo.variable(b, "b"))
+    got = llo.evaluate(root, np.dtype(I4))
+    want = (a.astype(np.float64) @ b.astype(np.float64)).astype(np.int64)
+    np.testing.assert_array_equal(want, got.astype(np.int64))
+
+
 @pytest.mark.parametrize("dtype", [F4, F8, I4])
 def test_matmul_gradients(mode, dtype):
     rng = np.random.default_rng(11)

@@ -1,1 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+mkdir -p gpurun_out/s12
+tools/probes/bin/powf_probe | tee gpurun_out/s12/powf_probe.txt

@@ -1,7 +1,8 @@
 #!/bin/bash
 # Round profile capture (run under gpurun): one ncu --set full capture per hot
 # kernel, exported as text / csv (the .ncu-rep files are too large to return),
-# plus the launch list of a short bench run.
+# a digest of all of them (summary.json), and the launch list of a short bench
+# run.  Every capture runs only after the same command exited 0 without ncu.
 # usage: tools/capture_profiles.sh <outdir>
 set -u
 OUT=${1:-gpurun_out/profiles}
@@ -16,16 +17,20 @@ cap () {  # name, kernel regex, command...
 	echo "$name: done"
 }
 cap chain vm_pair4 python tools/prof_cases.py --case chain --iters 2
+ncu -i /tmp/prof_chain.ncu-rep --page source --csv 2>/dev/null | python tools/ncu_hot.py 30 > "$OUT/chain_hot.txt"
 cap exp vm_flat python tools/prof_cases.py --case exp --iters 2
 cap add vm_flat python tools/prof_cases.py --case add --iters 2
+cap mulext vm_flat python tools/prof_cases.py --case mulext --iters 2
 cap permute vm_tile4 python tools/prof_cases.py --case permute --iters 2
 cap rsum_cols fold python tools/prof_cases.py --case rsum_cols --iters 2
 cap rsum_rows fold python tools/prof_cases.py --case rsum_rows --iters 2
 cap rsum_all fold python tools/prof_cases.py --case rsum_all --iters 2
 cap sgemm_nn sgemm_tma python tools/gemm_bench.py --size 4096 --layouts nn --iters 1
+cap sgemm_persist sgemm_persist python tools/gemm_bench.py --mnk 8192,1024,784 --layouts nn --iters 1
 cap dgemm_nn dgemm_tma python tools/gemm_bench.py --size 4096 --dtype f64 --layouts nn --iters 1
 cap tf32x3_nn tf32x3 python tools/gemm_bench.py --size 4096 --precision 1 --layouts nn --iters 1
+python tools/summarize_profiles.py "$OUT" > "$OUT/summary.json"
 python bench.py --steps 3 --warmup 3 --skip-cpu > "$OUT/plain_bench.log" 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
 	--log-file "$OUT/launches_bench.csv" python bench.py --steps 3 --warmup 3 --skip-cpu > "$OUT/ncu_bench.log" 2>&1
 echo "launch list: done"
