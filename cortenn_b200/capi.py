@@ -69,6 +69,9 @@ EXPORTS = {
     "llo_cuda_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "llo_cuda_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "llo_cuda_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "llo_cuda_h2d_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "llo_cuda_d2h_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "llo_cuda_event_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "llo_cuda_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "llo_cuda_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
     "llo_cuda_sync": (C.c_int, [C.c_void_p]),

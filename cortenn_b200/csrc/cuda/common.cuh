@@ -30,6 +30,11 @@ struct llo_cuda_ctx
 	int reduce_mode = LLO_REDUCE_TREE;
 	// device-side error flag raised by kernels that validate coordinates
 	int* dev_error = nullptr;
+	// copy-engine lanes of llo_cuda_h2d_async / llo_cuda_d2h_async (created on
+	// first use) and the events that order them against `stream`
+	cudaStream_t up_stream = nullptr;
+	cudaStream_t down_stream = nullptr;
+	cudaEvent_t lane_fence = nullptr;
 	// K8: NCCL communicator of the batch-sharded executor (comm.cu)
 	void* comm = nullptr;
 	int comm_rank = 0;

@@ -124,6 +124,14 @@ int llo_cuda_destroy (llo_cuda_ctx* ctx)
 	llo_cuda_comm_destroy(ctx);
 	cudaStreamSynchronize(ctx->stream);
 	cudaFree(ctx->dev_error);
+	if (nullptr != ctx->lane_fence)
+	{
+		cudaStreamSynchronize(ctx->up_stream);
+		cudaStreamSynchronize(ctx->down_stream);
+		cudaStreamDestroy(ctx->up_stream);
+		cudaStreamDestroy(ctx->down_stream);
+		cudaEventDestroy(ctx->lane_fence);
+	}
 	if (ctx->own_stream)
 	{
 		cudaStreamDestroy(ctx->stream);
@@ -234,6 +242,58 @@ int llo_cuda_d2h (llo_cuda_ctx* ctx, void* dst, const void* src, size_t bytes)
 	return check_device_flag(ctx);
 }
 
+static int ensure_lanes (llo_cuda_ctx* ctx)
+{
+	if (nullptr != ctx->lane_fence)
+	{
+		return LLO_OK;
+	}
+	LLO_CUDA_TRY(cudaSetDevice(ctx->device));
+	LLO_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+	LLO_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+	LLO_CUDA_TRY(cudaEventCreateWithFlags(&ctx->lane_fence, cudaEventDisableTiming));
+	return LLO_OK;
+}
+
+int llo_cuda_h2d_async (llo_cuda_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+	LLO_TRY(ensure_lanes(ctx));
+	// the upload lane joins the stream (dst was allocated in stream order) ...
+	LLO_CUDA_TRY(cudaEventRecord(ctx->lane_fence, ctx->stream));
+	LLO_CUDA_TRY(cudaStreamWaitEvent(ctx->up_stream, ctx->lane_fence, 0));
+	LLO_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes,
+		cudaMemcpyHostToDevice, ctx->up_stream));
+	// ... and the stream's later work waits for the upload
+	LLO_CUDA_TRY(cudaEventRecord(ctx->lane_fence, ctx->up_stream));
+	LLO_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->lane_fence, 0));
+	return LLO_OK;
+}
+
+int llo_cuda_d2h_async (llo_cuda_ctx* ctx, void* dst, const void* src, size_t bytes,
+	void** done)
+{
+	if (nullptr == done)
+	{
+		return fail(LLO_ERR_FATAL, "llo_cuda_d2h_async: null event pointer");
+	}
+	LLO_TRY(ensure_lanes(ctx));
+	LLO_CUDA_TRY(cudaEventRecord(ctx->lane_fence, ctx->stream));
+	LLO_CUDA_TRY(cudaStreamWaitEvent(ctx->down_stream, ctx->lane_fence, 0));
+	LLO_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes,
+		cudaMemcpyDeviceToHost, ctx->down_stream));
+	cudaEvent_t ev;
+	LLO_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+	LLO_CUDA_TRY(cudaEventRecord(ev, ctx->down_stream));
+	*done = (void*) ev;
+	return LLO_OK;
+}
+
+int llo_cuda_event_sync (llo_cuda_ctx*, void* event)
+{
+	LLO_CUDA_TRY(cudaEventSynchronize((cudaEvent_t) event));
+	return LLO_OK;
+}
+
 int llo_cuda_d2d (llo_cuda_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
 	LLO_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes,
@@ -249,6 +309,11 @@ int llo_cuda_memset (llo_cuda_ctx* ctx, void* dst, int byte, size_t bytes)
 
 int llo_cuda_sync (llo_cuda_ctx* ctx)
 {
+	if (nullptr != ctx->lane_fence)
+	{
+		LLO_CUDA_TRY(cudaStreamSynchronize(ctx->up_stream));
+		LLO_CUDA_TRY(cudaStreamSynchronize(ctx->down_stream));
+	}
 	return check_device_flag(ctx);
 }
 

@@ -49,6 +49,17 @@ struct GenericData final
 	/// Make the host mirror `data_` current and return it
 	char* fetch (void);
 
+	/// Start copying the elements to a (pinned) host mirror on the download
+	/// lane without waiting for it: later device work is not held up and an
+	/// upload of the next input runs at the same time.  wait() completes it.
+	void fetch_async (void);
+
+	/// Complete fetch_async (no-op otherwise) and return the host mirror
+	char* wait (void);
+
+	/// Completion event of a pending fetch_async
+	std::shared_ptr<void> pending_;
+
 	size_t nbytes (void) const
 	{
 		return (size_t) age::type_size(dtype_) * shape_.n_elems();
@@ -118,6 +129,14 @@ struct Variable final : public ade::iLeaf
 	/// Assign generic reference to data source
 	/// (error strings: llo/data.hpp:125-133)
 	Variable& operator = (GenericRef data);
+
+	/// Same checks and effect as `= data`, but the upload runs on the copy
+	/// lane (llo_cuda_h2d_async) into a fresh device buffer: evaluations
+	/// already queued keep reading the old one, evaluations queued afterwards
+	/// see the new values, and the caller does not wait.  `data` must be
+	/// pinned (llo.pinned_empty) and stay untouched until a later result has
+	/// been waited for.
+	void assign_async (GenericRef data);
 
 	/// Implementation of iTensor
 	const ade::Shape& shape (void) const override

@@ -177,6 +177,30 @@ char* GenericData::fetch (void)
 	return data_.get();
 }
 
+void GenericData::fetch_async (void)
+{
+	if (nullptr != data_ || nullptr == device_)
+	{
+		return;
+	}
+	llo_cuda_ctx* c = device::ctx();
+	data_ = device::host_alloc(nbytes());
+	void* event = nullptr;
+	device::check(llo_cuda_d2h_async(c, data_.get(), device_.get(), nbytes(), &event));
+	pending_ = std::shared_ptr<void>(event,
+		[c](void* ev) { llo_cuda_event_destroy(c, ev); });
+}
+
+char* GenericData::wait (void)
+{
+	if (nullptr != pending_)
+	{
+		device::check(llo_cuda_event_sync(device::ctx(), pending_.get()));
+		pending_ = nullptr;
+	}
+	return fetch();
+}
+
 Variable::Variable (const char* data, age::_GENERATED_DTYPE dtype,
 	ade::Shape shape, std::string label) :
 	label_(label), shape_(shape), dtype_(dtype)
@@ -280,6 +304,32 @@ Variable& Variable::operator = (GenericRef data)
 	}
 	std::memcpy(host_.get(), data.data_, nbytes());
 	return *this;
+}
+
+void Variable::assign_async (GenericRef data)
+{
+	if (false == data.shape_.compatible_after(shape(), 0))
+	{
+		logs::fatalf("cannot assign data of incompatible shaped %s to "
+			"internal data of shape %s", data.shape_.to_string().c_str(),
+			shape().to_string().c_str());
+	}
+	if (data.dtype_ != dtype_)
+	{
+		logs::fatalf("cannot assign data of incompatible types %s "
+			"(external) and %s (internal)",
+			age::name_type(data.dtype_).c_str(), age::name_type(dtype_).c_str());
+	}
+	fill_.clear();
+	++version_;
+	// a fresh buffer: queued evaluations still read the previous mirror,
+	// which returns to the pool in stream order once they are done
+	std::shared_ptr<char> raw = device::alloc(nbytes());
+	device::check(llo_cuda_h2d_async(device::ctx(), raw.get(), data.data_,
+		nbytes()));
+	mirrors_.clear();
+	mirrors_.push_back(Mirror{dtype_, version_, raw});
+	host_stale_ = true;
 }
 
 void Variable::materialize (void) const

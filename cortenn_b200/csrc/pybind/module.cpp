@@ -128,6 +128,27 @@ static void assign (llo::Variable* target, py::array data)
 	*target = llo::GenericRef((char*) info.ptr, shape, want);
 }
 
+/// assign, on the upload lane (the array must be pinned: llo.pinned_empty)
+static void assign_async (llo::Variable* target, py::array data)
+{
+	age::_GENERATED_DTYPE want =
+		(age::_GENERATED_DTYPE) target->type_code();
+	age::_GENERATED_DTYPE have = exact_dtype(data.dtype(), "assign");
+	if (0 == (data.flags() & py::array::c_style))
+	{
+		logs::fatal("assign_async needs a C-contiguous (pinned) array");
+	}
+	py::buffer_info info = data.request();
+	ade::Shape shape = p2cshape(info.shape);
+	if (have != want)
+	{
+		logs::fatalf("cannot assign data of incompatible types %s "
+			"(external) and %s (internal)",
+			age::name_type(have).c_str(), age::name_type(want).c_str());
+	}
+	target->assign_async(llo::GenericRef((char*) info.ptr, shape, want));
+}
+
 static age::_GENERATED_DTYPE eval_dtype (py::dtype dtype)
 {
 	return exact_dtype(dtype, "evaluate");
@@ -156,6 +177,13 @@ static py::array evaluate (ade::TensptrT tens, py::dtype dtype)
 	auto pshape = c2pshape(gdata.shape_);
 	return wrap_host(dtype, pshape, gdata.data_);
 }
+
+/// Result whose device->host copy is in flight (evaluate_async)
+struct PendingResult
+{
+	llo::GenericData data_;
+	py::dtype dtype_;
+};
 
 /// Device-resident result handle
 struct DeviceResult
@@ -221,6 +249,11 @@ PYBIND11_MODULE(_C, m)
 		{
 			pyllo::assign(self.get(), data);
 		}, "assign to variable")
+		.def("assign_async", [](llo::VarptrT self, py::array data)
+		{
+			pyllo::assign_async(self.get(), data);
+		}, "assign from a pinned array without waiting: the upload runs on "
+			"the copy lane, evaluations queued afterwards see the new values")
 		.def_readwrite("label", &llo::Variable::label_);
 
 	// ---- age: graph builders (llo/cfg/llo.json:125-531) ----
@@ -370,6 +403,31 @@ PYBIND11_MODULE(_C, m)
 		}, "uninitialised numpy array in page-locked host memory: "
 		"Variable.assign from it and evaluate() move data by DMA",
 		py::arg("shape"), py::arg("dtype") = py::dtype::of<double>());
+	py::class_<pyllo::PendingResult>(llo_m, "PendingResult")
+		.def("result", [](pyllo::PendingResult& self)
+		{
+			{
+				py::gil_scoped_release release;
+				self.data_.wait();
+			}
+			return pyllo::wrap_host(self.dtype_, pyllo::c2pshape(self.data_.shape_),
+				self.data_.data_);
+		}, "wait for the device->host copy and return the array");
+	llo_m.def("evaluate_async", [](T tens, py::dtype dtype)
+		{
+			age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);
+			pyllo::PendingResult out;
+			out.dtype_ = dtype;
+			{
+				py::gil_scoped_release release;
+				out.data_ = llo::eval_device(tens, ctype);
+				out.data_.fetch_async();
+			}
+			return out;
+		}, "queue the evaluation and the copy of its result to pinned host "
+			"memory; .result() waits.  With Variable.assign_async the upload of "
+			"the next input overlaps the download of the last result",
+		py::arg("tens"), py::arg("dtype") = py::dtype::of<double>());
 	llo_m.def("evaluate_device", [](T tens, py::dtype dtype)
 		{
 			age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);

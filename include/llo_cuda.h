@@ -91,6 +91,23 @@ int llo_cuda_host_free (llo_cuda_ctx* ctx, void* hptr);
 int llo_cuda_h2d (llo_cuda_ctx* ctx, void* dst, const void* src_host, size_t bytes);
 int llo_cuda_d2h (llo_cuda_ctx* ctx, void* dst_host, const void* src, size_t bytes);
 int llo_cuda_d2d (llo_cuda_ctx* ctx, void* dst, const void* src, size_t bytes);
+/* Copy-engine lanes: transfers that overlap each other (PCIe is full duplex)
+ * and the kernels already queued on the context's stream.  The reference
+ * copies synchronously (llo/python/llo.cpp:101-147); these serve a pipelined
+ * caller that uploads the next input while the last result drains.
+ *   h2d_async: `dst` must be a fresh allocation (nothing queued reads or
+ *     writes it).  The copy starts once the work queued on the stream so far
+ *     has finished; everything queued afterwards waits for it.  `src_host`
+ *     (pinned) must stay untouched until the next llo_cuda_sync /
+ *     llo_cuda_event_sync of a later download.
+ *   d2h_async: the copy starts once the work queued on the stream so far has
+ *     finished and does not hold up later work; `*done` receives an event to
+ *     pass to llo_cuda_event_sync (then llo_cuda_event_destroy).  `src` must
+ *     stay allocated until then.  Device-side validation errors surface at
+ *     the next llo_cuda_sync / llo_cuda_d2h, not here. */
+int llo_cuda_h2d_async (llo_cuda_ctx* ctx, void* dst, const void* src_host, size_t bytes);
+int llo_cuda_d2h_async (llo_cuda_ctx* ctx, void* dst_host, const void* src, size_t bytes, void** done);
+int llo_cuda_event_sync (llo_cuda_ctx* ctx, void* event);
 int llo_cuda_memset (llo_cuda_ctx* ctx, void* dst, int byte, size_t bytes);
 int llo_cuda_sync (llo_cuda_ctx* ctx);
 /* number of kernels this context has launched so far (bench `gpu_launches`) */

@@ -349,3 +349,41 @@ def test_program_with_a_tensor_and_its_transpose(side, extra):
     rooti = age.sub(age.mul(vi, vi), age.permute(vi, order))
     np.testing.assert_array_equal(llo.evaluate(rooti, np.dtype(np.int32)),
                                   xi * xi - np.swapaxes(xi, -1, -2))
+
+
+def test_pipelined_assign_and_evaluate_match_the_synchronous_path():
+    """Variable.assign_async + llo.evaluate_async: uploads on the copy lane into
+    fresh buffers, downloads on the other lane; results of a pipelined sequence
+    over CHANGING inputs equal the synchronous ones, step by step"""
+    rng = np.random.default_rng(83)
+    shape = (512, 768)
+    b = rng.uniform(0.5, 2.0, (shape[1],)).astype(F4)
+    vx = llo.variable(np.zeros(shape, F4), "x")
+    vb = llo.variable(b, "b")
+    root = age.add(age.mul(age.exp(vx), age.extend(vb, 1, [shape[0]])), age.neg(vx))
+    inputs = []
+    for k in range(5):
+        xp = llo.pinned_empty(list(shape), np.dtype(F4))
+        xp[...] = rng.uniform(0.5, 2.0, shape).astype(F4)
+        inputs.append(xp)
+    want = []
+    for xp in inputs:
+        vx.assign(xp)
+        want.append(llo.evaluate(root, np.dtype(F4)).copy())
+    pending, got = None, []
+    for xp in inputs:
+        vx.assign_async(xp)
+        nxt = llo.evaluate_async(root, np.dtype(F4))
+        if pending is not None:
+            got.append(pending.result())
+        pending = nxt
+    got.append(pending.result())
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
+    # the variable's host copy follows the last asynchronous assignment
+    llo.sync()
+    vx.assign(inputs[0])
+    np.testing.assert_array_equal(llo.evaluate(vx, np.dtype(F4)), inputs[0])
+    with pytest.raises(RuntimeError):
+        vx.assign_async(np.zeros((3, 3), F4))
