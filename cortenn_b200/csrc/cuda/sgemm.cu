@@ -496,8 +496,21 @@ sgemm_persist_kernel (const __grid_constant__ CUtensorMap map_a,
 
 // ---- one CTA per (tile, split): the hardware hands tiles to SMs -----------------
 
+// Two CTAs per SM when both operands are [k][row] tiles: that variant needs
+// 127 registers, so with a 3-stage ring (100 KB) two CTAs fit and every
+// scheduler has 4 warps to pick from instead of 2.
 template <bool AK, bool BKC>
-__global__ void __launch_bounds__(THREADS, 1)
+struct GridShape
+{
+	static constexpr int CTAS = (AK || BKC) ? 1 : 2;
+	static constexpr int ST = (AK || BKC) ? STAGES : 3;
+	static constexpr uint32_t AHEAD = ST - 2;
+	static constexpr size_t SMEM = 1024 /* alignment slack */ +
+		(size_t) ST * STAGE_BYTES + TAIL_PAD + 2 * ST * sizeof(uint64_t);
+};
+
+template <bool AK, bool BKC>
+__global__ void __launch_bounds__(THREADS, GridShape<AK,BKC>::CTAS)
 sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 	const __grid_constant__ CUtensorMap map_b,
 	const __grid_constant__ SgemmArgs args)
@@ -507,6 +520,8 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 	// (offset arithmetic on the __shared__ symbol keeps the address space,
 	// so tile reads compile to LDS rather than generic LD)
 	unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+	constexpr int STAGES = GridShape<AK,BKC>::ST;       // (shadow the file-level ones)
+	constexpr uint32_t LEAD = GridShape<AK,BKC>::AHEAD;
 	float* tiles_a = (float*) smem;
 	float* tiles_b = tiles_a + STAGES * A_STAGE_FLOATS;
 	uint64_t* full = (uint64_t*) (smem + (size_t) STAGES * STAGE_BYTES + TAIL_PAD);
@@ -828,11 +843,11 @@ template <bool AK, bool BKC>
 int launch_variant (llo_cuda_ctx* ctx, const CUtensorMap& ma,
 	const CUtensorMap& mb, const SgemmArgs& args, uint32_t splits)
 {
+	constexpr size_t smem = GridShape<AK,BKC>::SMEM;
 	LLO_CUDA_TRY(cudaFuncSetAttribute(sgemm_tma_kernel<AK,BKC>,
-		cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM_BYTES));
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	dim3 grid(args.tiles_m * args.tiles_n, splits);
-	sgemm_tma_kernel<AK,BKC><<<grid, THREADS, SMEM_BYTES,
-		ctx->stream>>>(ma, mb, args);
+	sgemm_tma_kernel<AK,BKC><<<grid, THREADS, smem, ctx->stream>>>(ma, mb, args);
 	return launched(ctx, "sgemm_tma_kernel");
 }
 
