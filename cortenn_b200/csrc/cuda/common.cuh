@@ -35,6 +35,16 @@ struct llo_cuda_ctx
 	cudaStream_t up_stream = nullptr;
 	cudaStream_t down_stream = nullptr;
 	cudaEvent_t lane_fence = nullptr;
+	// scratch arena of the GEMM drivers (struct Scratch): one grow-only block
+	// reused by every call -- the calls are ordered on `stream`, so handing
+	// the same bytes to the next call is safe, and nothing is allocated or
+	// freed per call once the high-water mark has been seen
+	char* arena = nullptr;
+	size_t arena_cap = 0;
+	size_t arena_used = 0;     // bytes handed out from the block
+	size_t arena_asked = 0;    // bytes asked for by the open scopes (may exceed cap)
+	size_t arena_want = 0;     // high-water mark of arena_asked
+	int arena_depth = 0;
 	// K8: NCCL communicator of the batch-sharded executor (comm.cu)
 	void* comm = nullptr;
 	int comm_rank = 0;
@@ -165,7 +175,11 @@ inline uint64_t n_elems (const uint64_t shape[LLO_RANK])
 /// Scratch device allocation released (stream-ordered) at scope exit
 struct Scratch final
 {
-	Scratch (llo_cuda_ctx* ctx) : ctx_(ctx) {}
+	Scratch (llo_cuda_ctx* ctx) : ctx_(ctx),
+		used_mark_(ctx->arena_used), asked_mark_(ctx->arena_asked)
+	{
+		++ctx_->arena_depth;
+	}
 
 	~Scratch (void)
 	{
@@ -173,13 +187,53 @@ struct Scratch final
 		{
 			cudaFreeAsync(p, ctx_->stream);
 		}
+		ctx_->arena_used = used_mark_;
+		ctx_->arena_asked = asked_mark_;
+		if (0 == --ctx_->arena_depth && ctx_->arena_want > ctx_->arena_cap)
+		{
+			// nobody holds arena pointers now; work already queued keeps
+			// the old block until it has run (stream-ordered free)
+			if (nullptr != ctx_->arena)
+			{
+				cudaFreeAsync(ctx_->arena, ctx_->stream);
+				ctx_->arena = nullptr;
+				ctx_->arena_cap = 0;
+			}
+			void* block = nullptr;
+			size_t cap = ctx_->arena_want + ctx_->arena_want / 8;
+			if (cudaSuccess == cudaMallocAsync(&block, cap, ctx_->stream))
+			{
+				ctx_->arena = (char*) block;
+				ctx_->arena_cap = cap;
+			}
+			else
+			{
+				cudaGetLastError(); // stay on per-call allocations
+				ctx_->arena_want = 0;
+			}
+		}
 	}
 
 	int get (void** out, size_t nbytes)
 	{
+		nbytes = (nbytes + 255) & ~(size_t) 255;
+		if (0 == nbytes)
+		{
+			nbytes = 256;
+		}
+		ctx_->arena_asked += nbytes;
+		if (ctx_->arena_asked > ctx_->arena_want)
+		{
+			ctx_->arena_want = ctx_->arena_asked;
+		}
+		if (nullptr != ctx_->arena && ctx_->arena_used + nbytes <= ctx_->arena_cap)
+		{
+			*out = ctx_->arena + ctx_->arena_used;
+			ctx_->arena_used += nbytes;
+			return LLO_OK;
+		}
 		void* p = nullptr;
-		cudaError_t err = cudaMallocAsync(&p,
-			nbytes > 0 ? nbytes : 16, ctx_->stream);
+		cudaError_t err = cudaMallocAsync(&p, nbytes, ctx_->stream);
 		if (cudaSuccess != err)
 		{
 			return fail_cuda(err, "scratch cudaMallocAsync");
@@ -191,6 +245,8 @@ struct Scratch final
 
 private:
 	llo_cuda_ctx* ctx_;
+	size_t used_mark_;
+	size_t asked_mark_;
 	std::vector<void*> ptrs_;
 };
 

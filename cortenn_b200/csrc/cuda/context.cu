@@ -124,6 +124,11 @@ int llo_cuda_destroy (llo_cuda_ctx* ctx)
 	llo_cuda_comm_destroy(ctx);
 	cudaStreamSynchronize(ctx->stream);
 	cudaFree(ctx->dev_error);
+	if (nullptr != ctx->arena)
+	{
+		cudaFreeAsync(ctx->arena, ctx->stream);
+		cudaStreamSynchronize(ctx->stream);
+	}
 	if (nullptr != ctx->lane_fence)
 	{
 		cudaStreamSynchronize(ctx->up_stream);

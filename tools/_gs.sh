@@ -1,8 +1,11 @@
-mkdir -p gpurun_out/s15
-run () { for mnk in 8192,8192,8192:nn 8192,8192,8192:tn 4096,4096,4096:nn 2048,2048,2048:nn 784,1024,8192:tn 1024,1024,8192:tn 8192,8192,1024:nt; do python tools/gemm_bench.py --mnk ${mnk%%:*} --layouts ${mnk##*:} --iters 5 2>&1 | grep TFLOP; done; }
-echo "== new (2 CTAs/SM for [k][row] operands)"; run
-cp cortenn_b200/libllo_cuda.so /tmp/new.so; cp tools/_old_libllo_cuda.so cortenn_b200/libllo_cuda.so
-echo "== old"; run
-cp /tmp/new.so cortenn_b200/libllo_cuda.so
-echo "== new again"; run
-python tools/gemm_bench.py --check --size 512 --iters 1 2>&1 | tail -2
+mkdir -p gpurun_out/s16
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/s16/bench.log 2> gpurun_out/s16/bench.err; tail -c 600 gpurun_out/s16/bench.err
+python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/s16/bench.log') if l.startswith('{')][0])
+w=d['workloads']
+print('chain', d['value'], 'e2e', d['e2e']['value'])
+for k in ('matmul_f32','matmul_f32_3xtf32','matmul_f64','mlp_grad_eval','mlp_grad_eval_3xtf32'):
+    print(k, {a:(round(b,3) if isinstance(b,float) else b) for a,b in w[k].items() if a in ('TFLOPs','ms','launches_per_eval','host_enqueue_ms')})
+PY
