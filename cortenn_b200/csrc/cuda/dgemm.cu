@@ -52,8 +52,11 @@ __device__ __forceinline__ int col_of (int tn, int j)
 	return BKC ? tn + 4 * j : tn * 2 + (j & 1) + 8 * (j >> 1);
 }
 
+// (two CTAs per SM when both operands are [k][row] tiles: that variant fits 128
+// registers, the 4-stage ring is 100 KB, and four warps per scheduler instead
+// of two keep the FP64 pipe fed)
 template <bool AK, bool BKC>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, (AK || BKC) ? 1 : 2)
 dgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 	const __grid_constant__ CUtensorMap map_b,
 	const __grid_constant__ DgemmArgs args)
