@@ -100,6 +100,24 @@ extern "C" int llo_cuda_gemm (llo_cuda_ctx* ctx, int dtype,
 		return fail(LLO_ERR_FATAL, "cannot gemm with an empty dimension");
 	}
 	GemmParams p = {M, N, K, a_rs, a_cs, b_rs, b_cs, c_rs, c_cs};
+	if (LLO_DT_FLOAT == dtype || (LLO_DT_DOUBLE == dtype && LLO_GEMM_EXACT == precision))
+	{
+		bool handled = false;
+		if (LLO_DT_FLOAT == dtype)
+		{
+			LLO_TRY(skinny_launch<float>(ctx, p, (float*) C, (const float*) A,
+				(const float*) B, handled));
+		}
+		else
+		{
+			LLO_TRY(skinny_launch<double>(ctx, p, (double*) C, (const double*) A,
+				(const double*) B, handled));
+		}
+		if (handled)
+		{
+			return LLO_OK;
+		}
+	}
 	if (LLO_DT_FLOAT == dtype)
 	{
 		bool handled = false;

@@ -30,6 +30,12 @@ int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p, float* C,
 int tf32x3_launch (llo_cuda_ctx* ctx, const GemmParams& p, float* C,
 	const float* A, const float* B, bool& handled);
 
+/// skinny.cu: products with one very short output dimension (N or M <= 16) and
+/// a long k: bandwidth-bound kernels, fp32 / fp64, same contract
+template <typename T>
+int skinny_launch (llo_cuda_ctx* ctx, const GemmParams& p, T* C, const T* A,
+	const T* B, bool& handled);
+
 /// dgemm.cu: DFMA path for fp64, same contract
 int dgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p, double* C,
 	const double* A, const double* B, bool& handled);
