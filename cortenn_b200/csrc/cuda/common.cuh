@@ -29,6 +29,8 @@ struct llo_cuda_ctx
 	uint64_t rand_offset = 0;
 	int reduce_mode = LLO_REDUCE_TREE;
 	// device-side error flag raised by kernels that validate coordinates
+	// ([0]); [1], [2]: work-unit counter / finished CTAs of the persistent tile
+	// kernels (self-resetting; one such kernel at a time per context)
 	int* dev_error = nullptr;
 	// copy-engine lanes of llo_cuda_h2d_async / llo_cuda_d2h_async (created on
 	// first use) and the events that order them against `stream`

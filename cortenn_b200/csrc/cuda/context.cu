@@ -102,14 +102,14 @@ int llo_cuda_init (int device, llo_cuda_ctx** out)
 		cudaMemPoolSetAttribute(pool,
 			cudaMemPoolAttrReleaseThreshold, &threshold);
 	}
-	err = cudaMalloc(&ctx->dev_error, sizeof(int));
+	err = cudaMalloc(&ctx->dev_error, 4 * sizeof(int));
 	if (cudaSuccess != err)
 	{
 		cudaStreamDestroy(ctx->stream);
 		delete ctx;
 		return fail_cuda(err, "cudaMalloc(error flag)");
 	}
-	cudaMemset(ctx->dev_error, 0, sizeof(int));
+	cudaMemset(ctx->dev_error, 0, 4 * sizeof(int));
 	*out = ctx;
 	return LLO_OK;
 }

@@ -557,7 +557,40 @@ __device__ __forceinline__ void run_tile (const VmParams& p,
 	}
 }
 
-/// Persistent: CTA c handles tiles c, c + grid, ...  With ALIGNED staging the
+/// Work-unit hand-out of the persistent tile kernels.  A CTA starts with unit
+/// blockIdx.x; further units come from a global counter (static c + grid
+/// strides left the SMs that sit further from L2 up to 11% behind the others:
+/// profiles/r1_permute_details.txt).  Thread 0 claims one unit ahead -- the
+/// atomic's latency hides under the current unit's work -- and publishes it
+/// through shared memory at the barrier that already ends every iteration.
+struct UnitClaim
+{
+	uint32_t* sched;
+	uint32_t* slot;     // shared word
+	uint32_t claimed;   // thread 0: the unit claimed for the iteration after next
+
+	__device__ __forceinline__ uint32_t claim (void) const
+	{
+		return gridDim.x + atomicAdd(sched, 1u);
+	}
+
+	/// the last CTA out resets the counter for the next launch
+	__device__ __forceinline__ void finish (void) const
+	{
+		if (0 == threadIdx.x)
+		{
+			__threadfence();
+			if (gridDim.x - 1 == atomicAdd(sched + 1, 1u))
+			{
+				sched[0] = 0;
+				sched[1] = 0;
+				__threadfence();
+			}
+		}
+	}
+};
+
+/// Persistent: CTA c handles tiles c, then whatever the counter hands out.  With ALIGNED staging the
 /// cp.async copies of the next tile fly while the current one is computed
 /// (two tile buffers); the scalar fallback stages and computes in turn.
 template <typename T, bool ALIGNED>
@@ -573,14 +606,25 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 	uint32_t o0, o1, brest;
 	if (ALIGNED)
 	{
+		__shared__ uint32_t next_slot;
+		UnitClaim units = {p.sched, &next_slot, 0};
 		uint32_t tile = blockIdx.x;
+		if (0 == threadIdx.x)
+		{
+			next_slot = units.claim();
+		}
 		tile_origin(p, tile, o0, o1, brest);
 		stage_tiles<T,true>(p, tiles, o0, o1, brest);
 		asm volatile("cp.async.commit_group;" ::: "memory");
+		__syncthreads();
+		uint32_t next = next_slot;
 		int buf = 0;
 		while (tile < p.total_tiles)
 		{
-			uint32_t next = tile + gridDim.x;
+			if (0 == threadIdx.x)
+			{
+				units.claimed = units.claim();
+			}
 			uint32_t n0 = 0, n1 = 0, nrest = 0;
 			if (next < p.total_tiles)
 			{
@@ -595,13 +639,19 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 			}
 			__syncthreads();
 			run_tile<T,false>(p, th, tiles + buf * buf_elems, spill, o0, o1, brest);
+			if (0 == threadIdx.x)
+			{
+				next_slot = units.claimed;
+			}
 			__syncthreads(); // everyone is done with this buffer
 			buf ^= 1;
 			tile = next;
+			next = next_slot;
 			o0 = n0;
 			o1 = n1;
 			brest = nrest;
 		}
+		units.finish();
 	}
 	else
 	{
@@ -708,12 +758,10 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 		}
 	};
 
-	uint32_t unit = blockIdx.x;
+	// (units go round-robin here: handing them out through the counter, which
+	// helps vm_tile4_kernel, measured 4% slower on this instruction-bound kernel)
+	uint32_t unit = blockIdx.x;    // (the grid never exceeds the unit count)
 	uint32_t i, j, brest;
-	if (unit >= total)
-	{
-		return;
-	}
 	unit_of(unit, i, j, brest);
 	stage_pair(0, i, j, brest);
 	asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1276,6 +1324,7 @@ static int launch_tile (llo_cuda_ctx* ctx, VmParams& p, int nstaged,
 	size_t spill, unsigned blocks)
 {
 	p.total_tiles = blocks;
+	p.sched = reinterpret_cast<uint32_t*>(ctx->dev_error + 1);
 	using G = VmGeom<T>;
 	if constexpr (4 == sizeof(T))
 	{

@@ -157,6 +157,9 @@ struct VmParams
 	int32_t pair_mode;      // one CTA computes output tiles (i,j) and (j,i) from
 	                        // the two input tiles it staged once (vm_pair4_kernel)
 	int32_t tile_input;     // pair mode: index of the staged input
+	// persistent tile kernels: {next work unit, finished CTAs}; CTAs claim
+	// their units from it so faster SMs take more (the last CTA out re-arms it)
+	uint32_t* sched;
 	uint64_t dims[LLO_RANK];
 	int64_t out_stride[LLO_RANK]; // dense strides of the collapsed dims
 	FastDiv div[LLO_RANK];
