@@ -362,7 +362,10 @@ def test_gemm(ctx, dtype, layout):
     (2000, 1300, 100),    # the same, ragged edges
     (2432, 2432, 40),     # 361 tiles: two full rounds + a split tail
     (128, 256, 4096),     # two tiles, long k: split-K with the fixed-order fold
-    (1000, 10, 3000),     # skinny output (re-pitched operand)
+    (1000, 10, 3000),     # skinny output: warp-per-rows / k-split column kernels (skinny.cu)
+    (10, 1000, 3000),     # skinny the other way round (transposed problem)
+    (4100, 16, 300),      # widest skinny output, ragged rows
+    (3000, 1, 1000),      # matrix-vector
 ])
 def test_gemm_schedules(ctx, dtype, layout, mnk):
     """every work decomposition of the TMA GEMMs (tile grid, split-K, persistent
