@@ -92,7 +92,6 @@ EXPORTS = {
     "llo_cuda_reduce_view": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(View),
                                        C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.c_int, C.c_int]),
     "llo_cuda_elementwise": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(View), C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(Insn), C.c_int]),
-    "llo_cuda_elementwise_reduce": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.POINTER(View), C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(Insn), C.c_int]),
     "llo_cuda_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
                                 C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                 C.c_void_p, C.c_int64, C.c_int64, C.c_int]),

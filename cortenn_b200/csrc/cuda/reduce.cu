@@ -732,13 +732,6 @@ extern "C" int llo_cuda_reduce (llo_cuda_ctx* ctx, int opcode, int dtype,
 	return reduce_launch(ctx, opcode, dtype, out, in, desc, 0, mode);
 }
 
-extern "C" int llo_cuda_elementwise_reduce (llo_cuda_ctx*, int, void*,
-	const uint64_t*, int, int, const llo_cuda_view*, int,
-	const double*, int, const llo_cuda_insn*, int)
-{
-	return fail(LLO_ERR_FATAL, "llo_cuda_elementwise_reduce: not built yet");
-}
-
 extern "C" int llo_cuda_reduce_view (llo_cuda_ctx* ctx, int opcode, int dtype,
 	void* out, const uint64_t outshape[LLO_RANK], const llo_cuda_view* src,
 	int nfold, const uint64_t* fold_size, const int64_t* fold_stride,

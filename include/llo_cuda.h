@@ -200,15 +200,6 @@ int llo_cuda_reduce_view (llo_cuda_ctx* ctx, int opcode, int dtype, void* out,
 	const uint64_t outshape[LLO_RANK], const llo_cuda_view* src,
 	int nfold, const uint64_t* fold_size, const int64_t* fold_stride,
 	int accumulate, int mode);
-/* Same program as llo_cuda_elementwise, but the result is folded over output
- * dims >= first_dim with `reduce_opcode` (SUM PROD MIN MAX) instead of being
- * stored: out has shape outshape[0:first_dim]. */
-int llo_cuda_elementwise_reduce (llo_cuda_ctx* ctx, int dtype, void* out,
-	const uint64_t outshape[LLO_RANK], int first_dim, int reduce_opcode,
-	const llo_cuda_view* inputs, int ninputs,
-	const double* consts, int nconsts,
-	const llo_cuda_insn* program, int ninsns);
-
 /* ---- K6/K7: GEMM the composed matmul sub-graph lowers to
  *      (llo/src/helper.cpp:67-97).  C[m,n] = sum_k A[m,k]*B[k,n], k ascending
  *      per output in FFMA/DFMA order within a k-tile.  Element (m,k) of A is
