@@ -45,12 +45,20 @@ def main():
                   program((capi.VM_LOAD, 0), ("EXP", 0), (capi.VM_LOAD, 1), ("PROD", 0), (capi.VM_LOAD, 2), ("SUM", 0))),
     }
     small = ctx.alloc(side * 16)
-    if args.case in cases:
-        views, (prog, nprog) = cases[args.case]
+    # the chain over the reference-representable shape [128,128,128,128] (needs log2n = 28)
+    shape4 = capi.shape8([128, 128, 128, 128])
+    dense4 = [1, 128, 128 * 128, 128 * 128 * 128]
+    cases4 = {
+        "chain4": ([view(x, dense4), view(b, [1, 0, 0, 0]), view(x, [128, 1, 128 * 128, 128 * 128 * 128])],
+                   program((capi.VM_LOAD, 0), ("EXP", 0), (capi.VM_LOAD, 1), ("PROD", 0), (capi.VM_LOAD, 2), ("SUM", 0))),
+    }
+    if args.case in cases or args.case in cases4:
+        views, (prog, nprog) = (cases if args.case in cases else cases4)[args.case]
         arr = (capi.View * len(views))(*views)
+        oshape = shape2 if args.case in cases else shape4
 
         def run():
-            capi.check(lib.llo_cuda_elementwise(ctx.handle, F4, out, shape2, arr, len(views), None, 0, prog, nprog))
+            capi.check(lib.llo_cuda_elementwise(ctx.handle, F4, out, oshape, arr, len(views), None, 0, prog, nprog))
     elif args.case == "rsum_cols":
         def run():
             capi.check(lib.llo_cuda_reduce(ctx.handle, capi.OPCODES["SUM"], F4, small, x, shape2, 1, 0))
