@@ -223,20 +223,18 @@ __device__ __forceinline__ void cp_async16_full (uint32_t dst, const void* src)
 __device__ __forceinline__ int32_t rest_offset32 (const VmParams& p,
 	const int64_t (&stride)[LLO_RANK], uint32_t brest)
 {
-	// (the slowest dim takes what is left: no division for it, and none at
-	// all for the usual single extra dim)
+	if (p.ndims <= 3)
+	{
+		// the usual cases: no extra dim, or one (its coordinate is brest)
+		return p.ndims < 3 ? 0 : (int32_t) brest * (int32_t) stride[2];
+	}
 	int32_t off = 0;
-	int last = p.ndims - 1;
-	for (int d = 2; d < last; ++d)
+	for (int d = 2; d < p.ndims; ++d)
 	{
 		uint32_t dim = (uint32_t) p.dims[d];
 		uint32_t q = brest / dim;
 		off += (int32_t) (brest - q * dim) * (int32_t) stride[d];
 		brest = q;
-	}
-	if (last >= 2)
-	{
-		off += (int32_t) brest * (int32_t) stride[last];
 	}
 	return off;
 }

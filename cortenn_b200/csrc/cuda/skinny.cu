@@ -18,6 +18,7 @@
 ///
 
 #include <algorithm>
+#include <type_traits>
 #include <utility>
 
 #include "gemm.cuh"
@@ -37,100 +38,141 @@ __device__ __forceinline__ T fma_t (T a, T b, T c)
 	else { return fma(a, b, c); }
 }
 
-// ---- skinny output, A rows contiguous along k: one warp per R rows ----------------
-// B is staged chunk by chunk (SKINNY_KC k's) in shared memory with an odd row
-// pitch; lane l multiplies k = l, l + 32, ... of the chunk (so a warp reads 128
-// contiguous bytes of each A row per step and conflict-free words of B), the
-// per-lane sums run in ascending k and the 32 of them fold through a fixed
-// xor-shuffle tree
+// ---- skinny output, A rows contiguous along k: a warp per R rows at a time -------
+// B is staged chunk by chunk (skinny_kc k's) in shared memory TRANSPOSED,
+// bs[n][k]: lane l multiplies the E = 16 / sizeof(T) consecutive k at
+// E (l + 32 i) of the chunk, so it reads 16 bytes of each of its A rows per
+// step (a warp: 512 contiguous bytes per row) and one LDS.128 per column of B
+// (consecutive lanes, consecutive 16 bytes: conflict-free).  Per-lane sums run
+// in ascending k; the 32 of them fold through a fixed xor-shuffle tree.  Each
+// warp walks `groups` row groups per staged chunk to amortise the staging.
 
 // k's of B staged at a time: 512 (fp32) / 256 (fp64), <= 35 KB of shared memory
 template <typename T>
 constexpr int skinny_kc (void) { return 2048 / (int) sizeof(T); }
-constexpr int SKINNY_PITCH = SKINNY_MAX + 1;
 
-template <typename T, int R>
+template <typename T, int R, int GROUPS>
 __global__ void __launch_bounds__(256)
 skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
-	const T* __restrict__ B, GemmParams p)
+	const T* __restrict__ B, GemmParams p, int a_vec)
 {
-	constexpr int SKINNY_KC = skinny_kc<T>();
-	__shared__ T bs[SKINNY_KC * SKINNY_PITCH];
+	constexpr int E = 16 / (int) sizeof(T);
+	constexpr int KC = skinny_kc<T>();
+	constexpr int PITCH = KC + E;
+	using V = typename std::conditional<8 == sizeof(T), double2, float4>::type;
+	__shared__ __align__(16) T bs[SKINNY_MAX * PITCH];
 	const int lane = threadIdx.x & 31;
-	const uint64_t row0 = ((uint64_t) blockIdx.x * 8 + (threadIdx.x >> 5)) * R;
+	const int warp = threadIdx.x >> 5;
 	const int N = (int) p.N;
 	const uint32_t K = (uint32_t) p.K;
-	T acc[R][SKINNY_MAX];
+	const uint64_t cta_row0 = (uint64_t) blockIdx.x * (8 * R * GROUPS);
+	T acc[GROUPS][R][SKINNY_MAX];
 #pragma unroll
-	for (int r = 0; r < R; ++r)
+	for (int g = 0; g < GROUPS; ++g)
 	{
 #pragma unroll
-		for (int n = 0; n < SKINNY_MAX; ++n)
+		for (int r = 0; r < R; ++r)
 		{
-			acc[r][n] = T(0);
-		}
-	}
-	const T* arow[R];
-#pragma unroll
-	for (int r = 0; r < R; ++r)
-	{
-		uint64_t m = row0 + r < p.M ? row0 + r : p.M - 1;
-		arow[r] = A + (int64_t) m * p.a_rs;
-	}
-	for (uint32_t kc = 0; kc < K; kc += SKINNY_KC)
-	{
-		uint32_t len = min((uint32_t) SKINNY_KC, K - kc);
-		__syncthreads();
-		for (uint32_t i = threadIdx.x; i < len * (uint32_t) N; i += 256)
-		{
-			uint32_t k = i / (uint32_t) N;
-			uint32_t n = i - k * (uint32_t) N;
-			bs[k * SKINNY_PITCH + n] =
-				__ldg(B + (int64_t) (kc + k) * p.b_rs + (int64_t) n * p.b_cs);
-		}
-		__syncthreads();
-#pragma unroll 2
-		for (uint32_t k = (uint32_t) lane; k < len; k += 32)
-		{
-			T a[R];
-#pragma unroll
-			for (int r = 0; r < R; ++r)
-			{
-				a[r] = __ldcs(arow[r] + kc + k);
-			}
-			const T* brow = bs + k * SKINNY_PITCH;
 #pragma unroll
 			for (int n = 0; n < SKINNY_MAX; ++n)
 			{
-				if (n < N)
-				{
-					T bv = brow[n];
+				acc[g][r][n] = T(0);
+			}
+		}
+	}
+	for (uint32_t kc = 0; kc < K; kc += KC)
+	{
+		uint32_t len = min((uint32_t) KC, K - kc);
+		uint32_t padded = (len + E - 1) / E * E;
+		__syncthreads();
+		// thread t stages column t % 16 of rows t / 16, + 16, ... (zero beyond N / len)
+		{
+			int n = threadIdx.x & (SKINNY_MAX - 1);
+			for (uint32_t k = threadIdx.x / SKINNY_MAX; k < padded; k += 256 / SKINNY_MAX)
+			{
+				bs[n * PITCH + k] = (n < N && k < len) ?
+					__ldg(B + (int64_t) (kc + k) * p.b_rs + (int64_t) n * p.b_cs) : T(0);
+			}
+		}
+		__syncthreads();
 #pragma unroll
-					for (int r = 0; r < R; ++r)
+		for (int g = 0; g < GROUPS; ++g)
+		{
+			uint64_t row0 = cta_row0 + (uint64_t) (g * 8 + warp) * R;
+			if (row0 >= p.M)
+			{
+				continue;
+			}
+			for (uint32_t k0 = (uint32_t) lane * E; k0 < padded; k0 += 32 * E)
+			{
+				T a[R][E];
+#pragma unroll
+				for (int r = 0; r < R; ++r)
+				{
+					uint64_t m = row0 + r < p.M ? row0 + r : p.M - 1;
+					const T* src = A + (int64_t) m * p.a_rs + kc + k0;
+					if (a_vec && k0 + E <= len)
 					{
-						acc[r][n] = fma_t(a[r], bv, acc[r][n]);
+						V v = __ldcs(reinterpret_cast<const V*>(src));
+						const T* t = reinterpret_cast<const T*>(&v);
+#pragma unroll
+						for (int e = 0; e < E; ++e)
+						{
+							a[r][e] = t[e];
+						}
+					}
+					else
+					{
+#pragma unroll
+						for (int e = 0; e < E; ++e)
+						{
+							a[r][e] = k0 + e < len ? __ldg(src + e) : T(0);
+						}
+					}
+				}
+#pragma unroll
+				for (int n = 0; n < SKINNY_MAX; ++n)
+				{
+					if (n < N)
+					{
+						V bv = *reinterpret_cast<const V*>(bs + n * PITCH + k0);
+						const T* bt = reinterpret_cast<const T*>(&bv);
+#pragma unroll
+						for (int e = 0; e < E; ++e)
+						{
+#pragma unroll
+							for (int r = 0; r < R; ++r)
+							{
+								acc[g][r][n] = fma_t(a[r][e], bt[e], acc[g][r][n]);
+							}
+						}
 					}
 				}
 			}
 		}
 	}
 #pragma unroll
-	for (int r = 0; r < R; ++r)
+	for (int g = 0; g < GROUPS; ++g)
 	{
+		uint64_t row0 = cta_row0 + (uint64_t) (g * 8 + warp) * R;
 #pragma unroll
-		for (int n = 0; n < SKINNY_MAX; ++n)
+		for (int r = 0; r < R; ++r)
 		{
-			if (n < N)
-			{
-				T v = acc[r][n];
 #pragma unroll
-				for (int off = 16; off > 0; off >>= 1)
+			for (int n = 0; n < SKINNY_MAX; ++n)
+			{
+				if (n < N)
 				{
-					v = v + __shfl_xor_sync(0xffffffffu, v, off);
-				}
-				if (0 == lane && row0 + r < p.M)
-				{
-					C[(int64_t) (row0 + r) * p.c_rs + (int64_t) n * p.c_cs] = v;
+					T v = acc[g][r][n];
+#pragma unroll
+					for (int off = 16; off > 0; off >>= 1)
+					{
+						v = v + __shfl_xor_sync(0xffffffffu, v, off);
+					}
+					if (0 == lane && row0 + r < p.M)
+					{
+						C[(int64_t) (row0 + r) * p.c_rs + (int64_t) n * p.c_cs] = v;
+					}
 				}
 			}
 		}
@@ -258,10 +300,23 @@ int skinny_launch (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A0,
 	if (1 == p.a_cs)
 	{
 		// A rows run along k
-		constexpr int R = 4;
-		uint64_t warps = (p.M + R - 1) / R;
-		skinny_rows_kernel<T,R><<<(unsigned) ((warps + 7) / 8), 256, 0,
-			ctx->stream>>>(C, (const T*) A, (const T*) B, p);
+		// rows per CTA = 8 warps x R x GROUPS; more groups amortise the staging
+		// of B but need enough rows to fill the machine
+		constexpr int R = 2;
+		constexpr int E = 16 / (int) sizeof(T);
+		int a_vec = (0 == ((uintptr_t) A & 15u) && 0 == p.a_rs % E) ? 1 : 0;
+		uint64_t per1 = 8 * R;
+		constexpr int G = 4 == sizeof(T) ? 2 : 1; // (fp64 accumulators of 2 groups would spill)
+		if (G > 1 && p.M >= per1 * G * (uint64_t) ctx->sm_count * 2)
+		{
+			skinny_rows_kernel<T,R,G><<<(unsigned) ((p.M + per1 * G - 1) / (per1 * G)), 256, 0,
+				ctx->stream>>>(C, (const T*) A, (const T*) B, p, a_vec);
+		}
+		else
+		{
+			skinny_rows_kernel<T,R,1><<<(unsigned) ((p.M + per1 - 1) / per1), 256, 0,
+				ctx->stream>>>(C, (const T*) A, (const T*) B, p, a_vec);
+		}
 		handled = true;
 		return launched(ctx, "skinny_rows_kernel");
 	}
