@@ -12,9 +12,9 @@
 /// once, coalesced, stage the short one in shared memory, and sum in a fixed
 /// order (run-to-run deterministic; per-lane chains in ascending k, then a
 /// fixed shuffle tree / an ascending fold over k ranges).  Measured
-/// (tools/gemm_bench.py, same box): 8192x10x1024 75 -> 43 us, 1024x10x8192
-/// 70 -> 54 us, 65536x10x1024 384 -> 273 us, 1024x10x65536 356 -> 292 us --
-/// still latency-bound (about 1 TB/s), a round-2 item.
+/// (tools/gemm_bench.py): 8192x10x1024 75 -> 29 us, 1024x10x8192 70 -> 54 us,
+/// 65536x10x1024 384 -> 202 us, 1024x10x65536 356 -> 292 us -- still
+/// latency-bound (1.0-1.3 TB/s: no software pipelining of the A loads yet).
 ///
 
 #include <algorithm>
