@@ -531,7 +531,9 @@ __device__ __forceinline__ void run_tile (const VmParams& p,
 		FULL || (o0 + VM_TS <= (uint32_t) p.dims[0] &&
 			o1 + VM_TS <= (uint32_t) p.dims[1])};
 	T acc[G::V];
-	vm_exec<T>(acc, p, loader, spill);
+	// (the compact interpreter for the pair kernel, FULL = true, only:
+	// vm_tile4_kernel lost 2% to it on a plain permute)
+	vm_exec<T,Tile4Loader<T,FULL>,FULL>(acc, p, loader, spill);
 	int32_t os1 = (int32_t) p.out_stride[1];
 	T* out = static_cast<T*>(p.out) + rest_offset32(p, p.out_stride, brest) +
 		(int32_t) loader.c0 + (int32_t) loader.c1 * os1;

@@ -412,9 +412,72 @@ struct FlatLoader
 #define LLO_VM_EACH(BODY) _Pragma("unroll")\
 	for (int e = 0; e < V; ++e) { BODY; }
 
+/// The bulkiest operators (pow is > 100 instructions per element; tan / sin /
+/// cos carry their argument reduction, log its special cases) inlined 16 times
+/// each make up a third of every kernel that carries the interpreter.  The
+/// pair kernel is sensitive to code size (instruction-cache misses show up
+/// as `no_inst` stalls; the chain ran 2% faster on the same box without that
+/// third), so it (COMPACT = true) calls these operators out of line, four
+/// elements per call; the flat kernel keeps them inline (a stand-alone pow
+/// lost 4.5% to the calls), and so does vm_tile4_kernel (a plain permute lost
+/// 2%).
+template <typename T>
+struct VmQuad
+{
+	T a, b, c, d;
+};
+
+template <int SEL, typename T>
+__device__ __forceinline__ T vm_bulky (T acc, T x)
+{
+	if (VM_S_POW == SEL) { return m_pow(acc, x); }
+	if (VM_S_RPOW == SEL) { return m_pow(x, acc); }
+	if (VM_S_TAN == SEL) { return m_tan(acc); }
+	if (VM_S_SIN == SEL) { return m_sin(acc); }
+	if (VM_S_COS == SEL) { return m_cos(acc); }
+	return m_log(acc);
+}
+
+template <int SEL, typename T>
+__device__ __noinline__ VmQuad<T> vm_outlined (VmQuad<T> acc, VmQuad<T> x)
+{
+	VmQuad<T> r;
+	r.a = vm_bulky<SEL,T>(acc.a, x.a);
+	r.b = vm_bulky<SEL,T>(acc.b, x.b);
+	r.c = vm_bulky<SEL,T>(acc.c, x.c);
+	r.d = vm_bulky<SEL,T>(acc.d, x.d);
+	return r;
+}
+
+/// (unary operators have no operand: they are handed the accumulator twice so
+/// that the unloaded operand registers stay dead)
+#define LLO_VM_BULKY(SEL) if constexpr (COMPACT)\
+	{\
+		_Pragma("unroll")\
+		for (int q = 0; q < V; q += 4)\
+		{\
+			VmQuad<T> a4 = {acc[q], acc[q + 1], acc[q + 2], acc[q + 3]};\
+			VmQuad<T> x4 = a4;\
+			if constexpr (VM_S_POW == SEL || VM_S_RPOW == SEL)\
+			{\
+				x4 = VmQuad<T>{x[q], x[q + 1], x[q + 2], x[q + 3]};\
+			}\
+			VmQuad<T> r4 = vm_outlined<SEL,T>(a4, x4);\
+			acc[q] = r4.a; acc[q + 1] = r4.b; acc[q + 2] = r4.c; acc[q + 3] = r4.d;\
+		}\
+	}\
+	else if constexpr (VM_S_POW == SEL || VM_S_RPOW == SEL)\
+	{\
+		LLO_VM_EACH(acc[e] = (vm_bulky<SEL,T>(acc[e], x[e])))\
+	}\
+	else\
+	{\
+		LLO_VM_EACH(acc[e] = (vm_bulky<SEL,T>(acc[e], acc[e])))\
+	}
+
 /// Run the accumulator program for this thread's V outputs.  `spill` is the
 /// CTA's shared-memory spill area ([level][element][thread]).
-template <typename T, typename Loader>
+template <typename T, typename Loader, bool COMPACT = false>
 __device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
 	const VmParams& p, const Loader& loader, T* spill)
 {
@@ -471,11 +534,11 @@ __device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
 			case VM_S_ABS: LLO_VM_EACH(acc[e] = m_abs(acc[e])) break;
 			case VM_S_NEG: LLO_VM_EACH(acc[e] = m_neg(acc[e])) break;
 			case VM_S_ROUND: LLO_VM_EACH(acc[e] = m_round(acc[e])) break;
-			case VM_S_SIN: LLO_VM_EACH(acc[e] = m_sin(acc[e])) break;
-			case VM_S_COS: LLO_VM_EACH(acc[e] = m_cos(acc[e])) break;
-			case VM_S_TAN: LLO_VM_EACH(acc[e] = m_tan(acc[e])) break;
+			case VM_S_SIN: LLO_VM_BULKY(VM_S_SIN) break;
+			case VM_S_COS: LLO_VM_BULKY(VM_S_COS) break;
+			case VM_S_TAN: LLO_VM_BULKY(VM_S_TAN) break;
 			case VM_S_EXP: LLO_VM_EACH(acc[e] = m_exp(acc[e])) break;
-			case VM_S_LOG: LLO_VM_EACH(acc[e] = m_log(acc[e])) break;
+			case VM_S_LOG: LLO_VM_BULKY(VM_S_LOG) break;
 			case VM_S_SQRT: LLO_VM_EACH(acc[e] = m_sqrt(acc[e])) break;
 			case VM_S_SUM: LLO_VM_EACH(acc[e] = m_add(acc[e], x[e])) break;
 			case VM_S_PROD: LLO_VM_EACH(acc[e] = m_mul(acc[e], x[e])) break;
@@ -491,8 +554,8 @@ __device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
 			case VM_S_GT: LLO_VM_EACH(acc[e] = (T) (acc[e] > x[e])) break;
 			case VM_S_DIV: LLO_VM_EACH(acc[e] = m_div(acc[e], x[e])) break;
 			case VM_S_RDIV: LLO_VM_EACH(acc[e] = m_div(x[e], acc[e])) break;
-			case VM_S_POW: LLO_VM_EACH(acc[e] = m_pow(acc[e], x[e])) break;
-			case VM_S_RPOW: LLO_VM_EACH(acc[e] = m_pow(x[e], acc[e])) break;
+			case VM_S_POW: LLO_VM_BULKY(VM_S_POW) break;
+			case VM_S_RPOW: LLO_VM_BULKY(VM_S_RPOW) break;
 			default: break;
 		}
 	}
