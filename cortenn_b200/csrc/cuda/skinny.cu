@@ -12,9 +12,9 @@
 /// once, coalesced, stage the short one in shared memory, and sum in a fixed
 /// order (run-to-run deterministic; per-lane chains in ascending k, then a
 /// fixed shuffle tree / an ascending fold over k ranges).  Measured
-/// (tools/gemm_bench.py): 8192x10x1024 75 -> 29 us, 1024x10x8192 70 -> 54 us,
-/// 65536x10x1024 384 -> 202 us, 1024x10x65536 356 -> 292 us -- still
-/// latency-bound (1.0-1.3 TB/s: no software pipelining of the A loads yet).
+/// (tools/gemm_bench.py): 8192x10x1024 75 -> 30 us, 1024x10x8192 70 -> 54 us,
+/// 65536x10x1024 384 -> 176 us, 1024x10x65536 356 -> 292 us -- still
+/// latency-bound (1.0-1.5 TB/s).
 ///
 
 #include <algorithm>
@@ -103,9 +103,9 @@ skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
 			{
 				continue;
 			}
-			for (uint32_t k0 = (uint32_t) lane * E; k0 < padded; k0 += 32 * E)
+			// the loads of step i + 1 are issued before the FMAs of step i
+			auto fetch = [&] (T (&dst)[R][E], uint32_t k0)
 			{
-				T a[R][E];
 #pragma unroll
 				for (int r = 0; r < R; ++r)
 				{
@@ -118,7 +118,7 @@ skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
 #pragma unroll
 						for (int e = 0; e < E; ++e)
 						{
-							a[r][e] = t[e];
+							dst[r][e] = t[e];
 						}
 					}
 					else
@@ -126,9 +126,31 @@ skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
 #pragma unroll
 						for (int e = 0; e < E; ++e)
 						{
-							a[r][e] = k0 + e < len ? __ldg(src + e) : T(0);
+							dst[r][e] = k0 + e < len ? __ldg(src + e) : T(0);
 						}
 					}
+				}
+			};
+			T nxt[R][E];
+			if ((uint32_t) lane * E < padded)
+			{
+				fetch(nxt, (uint32_t) lane * E);
+			}
+			for (uint32_t k0 = (uint32_t) lane * E; k0 < padded; k0 += 32 * E)
+			{
+				T a[R][E];
+#pragma unroll
+				for (int r = 0; r < R; ++r)
+				{
+#pragma unroll
+					for (int e = 0; e < E; ++e)
+					{
+						a[r][e] = nxt[r][e];
+					}
+				}
+				if (k0 + 32 * E < padded)
+				{
+					fetch(nxt, k0 + 32 * E);
 				}
 #pragma unroll
 				for (int n = 0; n < SKINNY_MAX; ++n)

@@ -413,8 +413,9 @@ struct FlatLoader
 	for (int e = 0; e < V; ++e) { BODY; }
 
 /// The bulkiest operators (pow is > 100 instructions per element; tan / sin /
-/// cos carry their argument reduction, log its special cases) inlined 16 times
-/// each make up a third of every kernel that carries the interpreter.  The
+/// cos carry their argument reduction, log / div / sqrt / round their special
+/// cases) inlined 16 times each make up over a third of every kernel that
+/// carries the interpreter.  The
 /// pair kernel is sensitive to code size (instruction-cache misses show up
 /// as `no_inst` stalls; the chain ran 2% faster on the same box without that
 /// third), so it (COMPACT = true) calls these operators out of line, four
@@ -435,6 +436,10 @@ __device__ __forceinline__ T vm_bulky (T acc, T x)
 	if (VM_S_TAN == SEL) { return m_tan(acc); }
 	if (VM_S_SIN == SEL) { return m_sin(acc); }
 	if (VM_S_COS == SEL) { return m_cos(acc); }
+	if (VM_S_DIV == SEL) { return m_div(acc, x); }
+	if (VM_S_RDIV == SEL) { return m_div(x, acc); }
+	if (VM_S_SQRT == SEL) { return m_sqrt(acc); }
+	if (VM_S_ROUND == SEL) { return m_round(acc); }
 	return m_log(acc);
 }
 
@@ -458,7 +463,7 @@ __device__ __noinline__ VmQuad<T> vm_outlined (VmQuad<T> acc, VmQuad<T> x)
 		{\
 			VmQuad<T> a4 = {acc[q], acc[q + 1], acc[q + 2], acc[q + 3]};\
 			VmQuad<T> x4 = a4;\
-			if constexpr (VM_S_POW == SEL || VM_S_RPOW == SEL)\
+			if constexpr (VM_S_POW == SEL || VM_S_RPOW == SEL || VM_S_DIV == SEL || VM_S_RDIV == SEL)\
 			{\
 				x4 = VmQuad<T>{x[q], x[q + 1], x[q + 2], x[q + 3]};\
 			}\
@@ -466,7 +471,7 @@ __device__ __noinline__ VmQuad<T> vm_outlined (VmQuad<T> acc, VmQuad<T> x)
 			acc[q] = r4.a; acc[q + 1] = r4.b; acc[q + 2] = r4.c; acc[q + 3] = r4.d;\
 		}\
 	}\
-	else if constexpr (VM_S_POW == SEL || VM_S_RPOW == SEL)\
+	else if constexpr (VM_S_POW == SEL || VM_S_RPOW == SEL || VM_S_DIV == SEL || VM_S_RDIV == SEL)\
 	{\
 		LLO_VM_EACH(acc[e] = (vm_bulky<SEL,T>(acc[e], x[e])))\
 	}\
@@ -533,13 +538,13 @@ __device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
 				break;
 			case VM_S_ABS: LLO_VM_EACH(acc[e] = m_abs(acc[e])) break;
 			case VM_S_NEG: LLO_VM_EACH(acc[e] = m_neg(acc[e])) break;
-			case VM_S_ROUND: LLO_VM_EACH(acc[e] = m_round(acc[e])) break;
+			case VM_S_ROUND: LLO_VM_BULKY(VM_S_ROUND) break;
 			case VM_S_SIN: LLO_VM_BULKY(VM_S_SIN) break;
 			case VM_S_COS: LLO_VM_BULKY(VM_S_COS) break;
 			case VM_S_TAN: LLO_VM_BULKY(VM_S_TAN) break;
 			case VM_S_EXP: LLO_VM_EACH(acc[e] = m_exp(acc[e])) break;
 			case VM_S_LOG: LLO_VM_BULKY(VM_S_LOG) break;
-			case VM_S_SQRT: LLO_VM_EACH(acc[e] = m_sqrt(acc[e])) break;
+			case VM_S_SQRT: LLO_VM_BULKY(VM_S_SQRT) break;
 			case VM_S_SUM: LLO_VM_EACH(acc[e] = m_add(acc[e], x[e])) break;
 			case VM_S_PROD: LLO_VM_EACH(acc[e] = m_mul(acc[e], x[e])) break;
 			case VM_S_SUB: LLO_VM_EACH(acc[e] = m_sub(acc[e], x[e])) break;
@@ -552,8 +557,8 @@ __device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
 			case VM_S_NEQ: LLO_VM_EACH(acc[e] = (T) (acc[e] != x[e])) break;
 			case VM_S_LT: LLO_VM_EACH(acc[e] = (T) (acc[e] < x[e])) break;
 			case VM_S_GT: LLO_VM_EACH(acc[e] = (T) (acc[e] > x[e])) break;
-			case VM_S_DIV: LLO_VM_EACH(acc[e] = m_div(acc[e], x[e])) break;
-			case VM_S_RDIV: LLO_VM_EACH(acc[e] = m_div(x[e], acc[e])) break;
+			case VM_S_DIV: LLO_VM_BULKY(VM_S_DIV) break;
+			case VM_S_RDIV: LLO_VM_BULKY(VM_S_RDIV) break;
 			case VM_S_POW: LLO_VM_BULKY(VM_S_POW) break;
 			case VM_S_RPOW: LLO_VM_BULKY(VM_S_RPOW) break;
 			default: break;
