@@ -775,6 +775,13 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 	int buf = 0;
 	while (unit < total)
 	{
+		// One barrier per unit: once every thread's copies of this unit have
+		// landed and every thread is past it, the unit's tiles are visible to
+		// all AND everybody has finished computing from the other buffer, so
+		// the next unit may be staged into it right away (its copies fly under
+		// this unit's math).
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncthreads();
 		uint32_t next = unit + gridDim.x;
 		uint32_t ni = 0, nj = 0, nrest = 0;
 		if (next < total)
@@ -782,13 +789,7 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 			unit_of(next, ni, nj, nrest);
 			stage_pair(buf ^ 1, ni, nj, nrest);
 			asm volatile("cp.async.commit_group;" ::: "memory");
-			asm volatile("cp.async.wait_group 1;" ::: "memory");
 		}
-		else
-		{
-			asm volatile("cp.async.wait_group 0;" ::: "memory");
-		}
-		__syncthreads();
 		T* slot0 = tiles + buf * 2 * SLOT;
 		T* slot1 = slot0 + SLOT;
 		int halves = (i == j) ? 1 : 2;
@@ -804,7 +805,6 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 			uint32_t t1 = (i < j) ? (h ? i : j) : t0;
 			run_tile<T,true>(p, th, self, spill, t0 * VM_TS, t1 * VM_TS, brest, other);
 		}
-		__syncthreads(); // everyone is done with this buffer
 		buf ^= 1;
 		unit = next;
 		i = ni;
