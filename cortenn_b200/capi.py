@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libllo_cuda.so")
+# LLO_CUDA_LIB: same-box A/B runs of a variant build (tools/), never set in production
+LIB_PATH = os.environ.get("LLO_CUDA_LIB") or os.path.join(HERE, "libllo_cuda.so")
 
 RANK = 8
 MAT = 81

@@ -37,6 +37,12 @@ struct llo_cuda_ctx
 	cudaStream_t up_stream = nullptr;
 	cudaStream_t down_stream = nullptr;
 	cudaEvent_t lane_fence = nullptr;
+	// snapshots of dev_error[0] taken on the download lane right after each
+	// asynchronous result copy (pinned), checked by llo_cuda_event_sync
+	int* async_flags = nullptr;
+	static constexpr int async_slots = 256;
+	uint64_t async_next = 0;
+	std::vector<std::pair<cudaEvent_t,int>> async_pending;
 	// scratch arena of the GEMM drivers (struct Scratch): one grow-only block
 	// reused by every call -- the calls are ordered on `stream`, so handing
 	// the same bytes to the next call is safe, and nothing is allocated or

@@ -136,6 +136,7 @@ int llo_cuda_destroy (llo_cuda_ctx* ctx)
 		cudaStreamDestroy(ctx->up_stream);
 		cudaStreamDestroy(ctx->down_stream);
 		cudaEventDestroy(ctx->lane_fence);
+		cudaFreeHost(ctx->async_flags);
 	}
 	if (ctx->own_stream)
 	{
@@ -257,6 +258,9 @@ static int ensure_lanes (llo_cuda_ctx* ctx)
 	LLO_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
 	LLO_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
 	LLO_CUDA_TRY(cudaEventCreateWithFlags(&ctx->lane_fence, cudaEventDisableTiming));
+	LLO_CUDA_TRY(cudaHostAlloc((void**) &ctx->async_flags,
+		llo_cuda_ctx::async_slots * sizeof(int), cudaHostAllocDefault));
+	std::memset(ctx->async_flags, 0, llo_cuda_ctx::async_slots * sizeof(int));
 	return LLO_OK;
 }
 
@@ -286,16 +290,42 @@ int llo_cuda_d2h_async (llo_cuda_ctx* ctx, void* dst, const void* src, size_t by
 	LLO_CUDA_TRY(cudaStreamWaitEvent(ctx->down_stream, ctx->lane_fence, 0));
 	LLO_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes,
 		cudaMemcpyDeviceToHost, ctx->down_stream));
+	// the kernels that produced `src` may have raised the coordinate-error
+	// flag: snapshot it behind the copy, llo_cuda_event_sync reports it
+	int slot = (int) (ctx->async_next++ % llo_cuda_ctx::async_slots);
+	LLO_CUDA_TRY(cudaMemcpyAsync(ctx->async_flags + slot, ctx->dev_error,
+		sizeof(int), cudaMemcpyDeviceToHost, ctx->down_stream));
 	cudaEvent_t ev;
 	LLO_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 	LLO_CUDA_TRY(cudaEventRecord(ev, ctx->down_stream));
+	ctx->async_pending.emplace_back(ev, slot);
 	*done = (void*) ev;
 	return LLO_OK;
 }
 
-int llo_cuda_event_sync (llo_cuda_ctx*, void* event)
+int llo_cuda_event_sync (llo_cuda_ctx* ctx, void* event)
 {
 	LLO_CUDA_TRY(cudaEventSynchronize((cudaEvent_t) event));
+	if (nullptr == ctx)
+	{
+		return LLO_OK;
+	}
+	for (size_t i = 0; i < ctx->async_pending.size(); ++i)
+	{
+		if (ctx->async_pending[i].first != (cudaEvent_t) event)
+		{
+			continue;
+		}
+		int flag = ctx->async_flags[ctx->async_pending[i].second];
+		ctx->async_pending.erase(ctx->async_pending.begin() + i);
+		if (0 != flag)
+		{
+			cudaMemsetAsync(ctx->dev_error, 0, sizeof(int), ctx->stream);
+			return fail(LLO_ERR_FATAL, "cannot get index of bad coordinate "
+				"(a coordinate map left its tensor's shape)");
+		}
+		break;
+	}
 	return LLO_OK;
 }
 
@@ -349,8 +379,19 @@ int llo_cuda_event_elapsed_ms (llo_cuda_ctx*, void* start, void* stop, float* ms
 	return LLO_OK;
 }
 
-int llo_cuda_event_destroy (llo_cuda_ctx*, void* event)
+int llo_cuda_event_destroy (llo_cuda_ctx* ctx, void* event)
 {
+	if (nullptr != ctx)
+	{
+		for (size_t i = 0; i < ctx->async_pending.size(); ++i)
+		{
+			if (ctx->async_pending[i].first == (cudaEvent_t) event)
+			{
+				ctx->async_pending.erase(ctx->async_pending.begin() + i);
+				break;
+			}
+		}
+	}
 	LLO_CUDA_TRY(cudaEventDestroy((cudaEvent_t) event));
 	return LLO_OK;
 }

@@ -387,10 +387,12 @@ int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 	}
 	Scratch scratch(ctx);
 	// The kernels run fastest with both operands as [k][row] tiles (row
-	// vectors per k: no 4-k register fragments, fewer register-bank stalls;
-	// 55 vs 46-50 TFLOP/s fp32 at 8192^3).  When the other dimension is large
+	// vectors per k: no 4-k register fragments, 119 registers -> two CTAs per
+	// SM; 59 vs 50-52 TFLOP/s fp32).  When the other dimension is large
 	// enough to amortise one extra pass, a k-contiguous operand is transposed
-	// into scratch first (the products and their order are unchanged).
+	// into scratch first (the products and their order are unchanged):
+	// 65536x1024x784 50.4 -> 55.1 TFLOP/s including the pass (round 2 A/B,
+	// gpurun_out/gemm_ab2.log), break-even near 512.
 	auto relayout = [&] (const T*& base, int64_t& lead, bool& kc,
 		uint64_t rows, uint64_t other, uint64_t threshold) -> int
 	{
@@ -413,8 +415,13 @@ int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 	};
 	// (the pass costs ~8 bytes per operand element and buys ~10% of the
 	// 2 * other flops spent on each of them)
-	LLO_TRY(relayout(A, lead_a, ak, p.M, p.N, 2048));
-	LLO_TRY(relayout(B, lead_b, bk, p.N, p.M, 2048));
+	uint64_t relayout_min = 512;
+	if (const char* env = std::getenv("LLO_GEMM_RELAYOUT_MIN"))
+	{
+		relayout_min = (uint64_t) std::atoll(env); // experiments only
+	}
+	LLO_TRY(relayout(A, lead_a, ak, p.M, p.N, relayout_min));
+	LLO_TRY(relayout(B, lead_b, bk, p.N, p.M, relayout_min));
 	LLO_TRY(make_ready(ctx, scratch, A, lead_a, ak ? p.M : p.K, ak ? p.K : p.M));
 	LLO_TRY(make_ready(ctx, scratch, B, lead_b, bk ? p.N : p.K, bk ? p.K : p.N));
 	CUtensorMap ma, mb;

@@ -56,6 +56,81 @@ constexpr uint32_t LEAD = STAGES - 2;
 using SgemmArgs = tma::GemmArgs<float>;
 using namespace tma;
 
+/// Packed fp32 pair in one 64-bit register pair.  sm_100a multiplies two
+/// independent IEEE fp32 FMAs per issue slot (fma.rn.f32x2 -> SASS FFMA2);
+/// a pair built from the same scalar twice costs no instruction: ptxas folds
+/// it into the scalar-broadcast operand form (`FFMA2 Rd, Ra.F32, Rb.F32x2, Rc`).
+/// Each lane of the pair is the same single-rounding fused multiply-add as
+/// fmaf, so results are bit-identical to the scalar kernel's.
+using f32x2 = unsigned long long;
+
+__device__ __forceinline__ f32x2 pack2 (float lo, float hi)
+{
+	f32x2 r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+
+__device__ __forceinline__ void unpack2 (f32x2 v, float& lo, float& hi)
+{
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+__device__ __forceinline__ void fma2 (f32x2& acc, f32x2 a, f32x2 b)
+{
+	asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+/// acc(i, j) += a[i] * b[j] for the 8 x 8 outputs of a thread: 32 FFMA2.
+/// The pairs run along the operand whose fragment already holds neighbours
+/// in consecutive registers (a [k][row] tile read with LDS.128); the other
+/// operand is the broadcast scalar.
+///   PAIR_I false: acc2[i][jp] = (c[i][2jp], c[i][2jp+1])
+///   PAIR_I true : acc2[j][ip] = (c[2ip][j], c[2ip+1][j])
+template <bool PAIR_I>
+__device__ __forceinline__ void outer8x8 (f32x2 (&acc)[8][4], const float (&a)[8],
+	const float (&b)[8])
+{
+	f32x2 vp[4];
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+	{
+		vp[q] = PAIR_I ? pack2(a[2 * q], a[2 * q + 1]) : pack2(b[2 * q], b[2 * q + 1]);
+	}
+#pragma unroll
+	for (int s = 0; s < 8; ++s)
+	{
+		f32x2 sd = PAIR_I ? pack2(b[s], b[s]) : pack2(a[s], a[s]);
+#pragma unroll
+		for (int q = 0; q < 4; ++q)
+		{
+			fma2(acc[s][q], sd, vp[q]);
+		}
+	}
+}
+
+/// the 8 x 8 outputs as scalars
+template <bool PAIR_I>
+__device__ __forceinline__ void unpack8x8 (float (&c)[8][8], const f32x2 (&acc)[8][4])
+{
+#pragma unroll
+	for (int s = 0; s < 8; ++s)
+	{
+#pragma unroll
+		for (int q = 0; q < 4; ++q)
+		{
+			if (PAIR_I)
+			{
+				unpack2(acc[s][q], c[2 * q][s], c[2 * q + 1][s]);
+			}
+			else
+			{
+				unpack2(acc[s][q], c[s][2 * q], c[s][2 * q + 1]);
+			}
+		}
+	}
+}
+
 __device__ __forceinline__ float comp (const float4& v, int k)
 {
 	return 0 == k ? v.x : (1 == k ? v.y : (2 == k ? v.z : v.w));
@@ -94,6 +169,8 @@ sgemm_persist_kernel (const __grid_constant__ CUtensorMap map_a,
 	const __grid_constant__ SgemmArgs args)
 {
 	extern __shared__ __align__(1024) unsigned char smem_raw[];
+	// FFMA2 pairs run along i when only A's fragments hold row neighbours
+	constexpr bool PAIR_I = BKC && false == AK;
 	// 128-byte swizzled tiles must start on a 1024-byte boundary
 	// (offset arithmetic on the __shared__ symbol keeps the address space,
 	// so tile reads compile to LDS rather than generic LD)
@@ -207,14 +284,14 @@ sgemm_persist_kernel (const __grid_constant__ CUtensorMap map_a,
 	int wn = warp & 3;    // 0..3
 	int tm = lane >> 2;   // 0..7
 	int tn = lane & 3;    // 0..3
-	float acc[8][8];
+	f32x2 acc2[8][4];
 #pragma unroll
 	for (int i = 0; i < 8; ++i)
 	{
 #pragma unroll
-		for (int j = 0; j < 8; ++j)
+		for (int j = 0; j < 4; ++j)
 		{
-			acc[i][j] = 0.0f;
+			acc2[i][j] = 0ull;
 		}
 	}
 
@@ -372,15 +449,7 @@ sgemm_persist_kernel (const __grid_constant__ CUtensorMap map_a,
 						b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = lo.w;
 						b[4] = hi.x; b[5] = hi.y; b[6] = hi.z; b[7] = hi.w;
 					}
-#pragma unroll
-					for (int i = 0; i < 8; ++i)
-					{
-#pragma unroll
-						for (int j = 0; j < 8; ++j)
-						{
-							acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-						}
-					}
+					outer8x8<PAIR_I>(acc2, a, b);
 				}
 			}
 		}
@@ -395,6 +464,8 @@ sgemm_persist_kernel (const __grid_constant__ CUtensorMap map_a,
 		}
 
 		// ---- the unit is complete: registers -> C (or its partial tile) ----
+		float acc[8][8];
+		unpack8x8<PAIR_I>(acc, acc2);
 		if (c_unit >= args.full_tiles)
 		{
 			// partial product of a tail tile: dense [BM][BN], always in range
@@ -483,9 +554,9 @@ sgemm_persist_kernel (const __grid_constant__ CUtensorMap map_a,
 		for (int i = 0; i < 8; ++i)
 		{
 #pragma unroll
-			for (int j = 0; j < 8; ++j)
+			for (int j = 0; j < 4; ++j)
 			{
-				acc[i][j] = 0.0f;
+				acc2[i][j] = 0ull;
 			}
 		}
 		c_unit += grid;
@@ -516,6 +587,8 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 	const __grid_constant__ SgemmArgs args)
 {
 	extern __shared__ __align__(1024) unsigned char smem_raw[];
+	// FFMA2 pairs run along i when only A's fragments hold row neighbours
+	constexpr bool PAIR_I = BKC && false == AK;
 	// 128-byte swizzled tiles must start on a 1024-byte boundary
 	// (offset arithmetic on the __shared__ symbol keeps the address space,
 	// so tile reads compile to LDS rather than generic LD)
@@ -591,14 +664,19 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 	int wn = warp & 3;    // 0..3
 	int tm = lane >> 2;   // 0..7
 	int tn = lane & 3;    // 0..3
-	float acc[8][8];
+	// A warp whose 64 x 32 part of an edge tile lies wholly outside C keeps
+	// the barrier protocol (and its producer turns) but skips the math: the
+	// FMA pipe of its scheduler goes to the warp that shares it, so e.g. the
+	// 16-row last tile row of M = 784 costs half a tile, not a whole one.
+	const bool live = tile_m * BM + wm * 64 < args.M && tile_n * BN + wn * 32 < args.N;
+	f32x2 acc2[8][4];
 #pragma unroll
 	for (int i = 0; i < 8; ++i)
 	{
 #pragma unroll
-		for (int j = 0; j < 8; ++j)
+		for (int j = 0; j < 4; ++j)
 		{
-			acc[i][j] = 0.0f;
+			acc2[i][j] = 0ull;
 		}
 	}
 
@@ -637,6 +715,8 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 		const float4* As4 = (const float4*) (tiles_a + s * A_STAGE_FLOATS);
 		const float4* Bs4 = (const float4*) (tiles_b + s * B_STAGE_FLOATS);
 
+		if (live)
+		{
 		Frag<AK> fa;
 		Frag<BKC> fb;
 		// ---- prologue: fragments of k-group 0 / k 0 ----
@@ -749,18 +829,11 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 						b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = lo.w;
 						b[4] = hi.x; b[5] = hi.y; b[6] = hi.z; b[7] = hi.w;
 					}
-#pragma unroll
-					for (int i = 0; i < 8; ++i)
-					{
-#pragma unroll
-						for (int j = 0; j < 8; ++j)
-						{
-							acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-						}
-					}
+					outer8x8<PAIR_I>(acc2, a, b);
 				}
 			}
 		}
+		} // live
 		__syncwarp();
 		if (0 == lane)
 		{
@@ -769,6 +842,12 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 	}
 
 	// ---- epilogue: registers -> C ----
+	if (false == live)
+	{
+		return;
+	}
+	float acc[8][8];
+	unpack8x8<PAIR_I>(acc, acc2);
 	uint32_t m_base = tile_m * BM + wm * 64;
 	uint32_t n_base = tile_n * BN + wn * 32;
 #pragma unroll
@@ -877,7 +956,12 @@ int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p, float* C,
 		uint64_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
 		uint64_t tiles_t = ((p.N + BM - 1) / BM) * ((p.M + BN - 1) / BN);
 		uint64_t ktiles = (p.K + BK - 1) / BK;
-		persist = std::min(tiles, tiles_t) >= (uint64_t) ctx->sm_count && ktiles <= 64;
+		// (with FFMA2 and the [k][row] relayout the tile grid is ahead again
+		// once there are many rounds of tiles: 65536x1024x784 55.1 vs 53.5,
+		// 8192x1024x784 45.8 vs 49.2 TFLOP/s tile grid vs persistent)
+		uint64_t least = std::min(tiles, tiles_t);
+		persist = least >= (uint64_t) ctx->sm_count &&
+			least <= 12 * (uint64_t) ctx->sm_count && ktiles <= 64;
 	}
 	if (const char* env = std::getenv("LLO_GEMM_PERSIST"))
 	{

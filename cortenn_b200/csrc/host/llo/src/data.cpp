@@ -168,6 +168,10 @@ void GenericData::copyover (const char* indata, age::_GENERATED_DTYPE intype)
 
 char* GenericData::fetch (void)
 {
+	if (nullptr != pending_)
+	{
+		return wait(); // never hand out a half-written mirror
+	}
 	if (nullptr == data_ && nullptr != device_)
 	{
 		data_ = device::host_alloc(nbytes());
@@ -187,16 +191,27 @@ void GenericData::fetch_async (void)
 	data_ = device::host_alloc(nbytes());
 	void* event = nullptr;
 	device::check(llo_cuda_d2h_async(c, data_.get(), device_.get(), nbytes(), &event));
+	// The download runs on its own lane: neither buffer may go back to its
+	// pool (stream-ordered device free, pinned block reuse) before the DMA has
+	// finished.  The event's deleter therefore holds both and waits first, so
+	// dropping every copy of this GenericData without wait() stays safe.
+	std::shared_ptr<char> dev = device_;
+	std::shared_ptr<char> host = data_;
 	pending_ = std::shared_ptr<void>(event,
-		[c](void* ev) { llo_cuda_event_destroy(c, ev); });
+		[c, dev, host](void* ev)
+		{
+			llo_cuda_event_sync(c, ev);
+			llo_cuda_event_destroy(c, ev);
+		});
 }
 
 char* GenericData::wait (void)
 {
 	if (nullptr != pending_)
 	{
-		device::check(llo_cuda_event_sync(device::ctx(), pending_.get()));
+		std::shared_ptr<void> event = pending_;
 		pending_ = nullptr;
+		device::check(llo_cuda_event_sync(device::ctx(), event.get()));
 	}
 	return fetch();
 }
@@ -278,19 +293,12 @@ Variable& Variable::operator = (GenericRef data)
 	if (device::available())
 	{
 		// upload straight from the caller's buffer (one pass; DMA when the
-		// buffer is pinned); the host copy is refreshed only if asked for
-		std::shared_ptr<char> raw;
-		for (Mirror& m : mirrors_)
-		{
-			if (m.dtype_ == dtype_)
-			{
-				raw = m.data_;
-			}
-		}
-		if (nullptr == raw)
-		{
-			raw = device::alloc(nbytes());
-		}
+		// buffer is pinned); the host copy is refreshed only if asked for.
+		// Always into a FRESH buffer: results of earlier evaluations may share
+		// the old mirror (a root that is a leaf, or collapses to a view of
+		// one) and must keep their values; the old block returns to the pool
+		// in stream order once nobody holds it.
+		std::shared_ptr<char> raw = device::alloc(nbytes());
 		device::check(llo_cuda_h2d(device::ctx(), raw.get(), data.data_,
 			nbytes()));
 		mirrors_.clear(); // converted mirrors are out of date

@@ -757,11 +757,14 @@ struct Plan
 				}
 				args = kept;
 			}
-			else if (age::DIV == op && Kind::ELEM == args[0].node_->kind_ &&
+			else if (age::DIV == op && (age::FLOAT == dtype || age::DOUBLE == dtype) &&
+				Kind::ELEM == args[0].node_->kind_ &&
 				age::PROD == args[0].node_->opcode_)
 			{
 				// (x * y) / x -> y: the reference's product rule
-				// (llo/src/helper.cpp:18-33)
+				// (llo/src/helper.cpp:18-33).  Floating types only: integer
+				// products wrap and integer division truncates, so the
+				// quotient is not the other factor there.
 				PNode* prod = args[0].node_;
 				std::vector<PArg> factors;
 				for (const PArg& f : prod->args_)
@@ -962,7 +965,8 @@ struct Plan
 			size_t k = 0;
 			for (; k < prog.consts_.size(); ++k)
 			{
-				if (prog.consts_[k] == node->value_)
+				// bit patterns: -0.0 and 0.0 are different immediates
+				if (0 == std::memcmp(&prog.consts_[k], &node->value_, sizeof(double)))
 				{
 					break;
 				}

@@ -23,7 +23,7 @@ static std::map<std::string,long>& options (void)
 {
 	static std::map<std::string,long> opts = {
 		{"plan", env_default("LLO_PLAN", 1)},
-		{"simplify", env_default("LLO_SIMPLIFY", 1)},
+		{"simplify", env_default("LLO_SIMPLIFY", 0)},
 		{"recompute", env_default("LLO_RECOMPUTE", 0)},
 		{"tf32x3", env_default("LLO_TF32X3", 0)},
 		{"sequential_reduce", env_default("LLO_SEQUENTIAL_REDUCE", 0)},

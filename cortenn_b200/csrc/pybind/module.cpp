@@ -10,6 +10,12 @@
 ///            Tensor.__str__/shape()/children()   (llo/python/llo.cpp:156-215)
 /// numpy shapes are the reverse of ade shapes (llo/python/llo.cpp:18-34).
 ///
+/// Threading: like the reference's binding (which never releases the GIL,
+/// llo/python/llo.cpp) every call here holds the GIL for its whole duration.
+/// The evaluator context, the planner and Variable's device mirrors are
+/// single-threaded by contract (SURVEY.md 8b "Threading"); only comm_init,
+/// which blocks on the other ranks' processes, releases it.
+///
 /// Additions: evaluate() honours the exact numpy dtype
 /// (the reference only distinguishes 'f' -> DOUBLE and 'i' -> INT64, which
 /// the float64 / int64 defaults still select), unsigned dtypes are accepted,
@@ -169,11 +175,7 @@ static py::array wrap_host (py::dtype dtype, std::vector<py::ssize_t> pshape,
 static py::array evaluate (ade::TensptrT tens, py::dtype dtype)
 {
 	age::_GENERATED_DTYPE ctype = eval_dtype(dtype);
-	llo::GenericData gdata;
-	{
-		py::gil_scoped_release release;
-		gdata = llo::eval(tens, ctype);
-	}
+	llo::GenericData gdata = llo::eval(tens, ctype);
 	auto pshape = c2pshape(gdata.shape_);
 	return wrap_host(dtype, pshape, gdata.data_);
 }
@@ -357,6 +359,33 @@ PYBIND11_MODULE(_C, m)
 	llo_m.def("derive", [](T root, T target)
 		{ return llo::derive(root, target.get()); },
 		"derive tensor with respect to some derive");
+	// graph -> graph optimisation (llo/optimize.hpp); explicit, never implied
+	llo_m.attr("OPT_ONE_MUL") = (unsigned) llo::OPT_ONE_MUL;
+	llo_m.attr("OPT_ZERO_ADD") = (unsigned) llo::OPT_ZERO_ADD;
+	llo_m.attr("OPT_POW_ONE") = (unsigned) llo::OPT_POW_ONE;
+	llo_m.attr("OPT_SINGLE") = (unsigned) llo::OPT_SINGLE;
+	llo_m.attr("OPT_CSE") = (unsigned) llo::OPT_CSE;
+	llo_m.attr("OPT_DIV_CANCEL") = (unsigned) llo::OPT_DIV_CANCEL;
+	llo_m.attr("OPT_EXACT") = (unsigned) llo::OPT_EXACT;
+	llo_m.attr("OPT_ALL") = (unsigned) llo::OPT_ALL;
+	llo_m.def("optimize", [](std::vector<T> roots, unsigned passes)
+		{
+			llo::OptReport report;
+			ade::TensT out = llo::optimize(roots, passes, &report);
+			py::dict rep;
+			rep["functors_before"] = report.functors_before_;
+			rep["functors_after"] = report.functors_after_;
+			rep["one_mul"] = report.one_mul_;
+			rep["zero_add"] = report.zero_add_;
+			rep["pow_one"] = report.pow_one_;
+			rep["single"] = report.single_;
+			rep["shared"] = report.shared_;
+			rep["div_cancel"] = report.div_cancel_;
+			return py::make_tuple(out, rep);
+		}, "rewrite the graphs under `roots` with the selected passes "
+		"(OPT_EXACT: value-preserving; OPT_DIV_CANCEL: (x*y)/x -> y, inexact, "
+		"floating point only); returns (new roots, report)",
+		py::arg("roots"), py::arg("passes") = (unsigned) llo::OPT_ALL);
 	llo_m.def("seed", [](size_t seed)
 		{
 			llo::device::check(llo_cuda_seed(llo::device::ctx(), seed));
@@ -406,10 +435,7 @@ PYBIND11_MODULE(_C, m)
 	py::class_<pyllo::PendingResult>(llo_m, "PendingResult")
 		.def("result", [](pyllo::PendingResult& self)
 		{
-			{
-				py::gil_scoped_release release;
-				self.data_.wait();
-			}
+			self.data_.wait();
 			return pyllo::wrap_host(self.dtype_, pyllo::c2pshape(self.data_.shape_),
 				self.data_.data_);
 		}, "wait for the device->host copy and return the array");
@@ -418,11 +444,8 @@ PYBIND11_MODULE(_C, m)
 			age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);
 			pyllo::PendingResult out;
 			out.dtype_ = dtype;
-			{
-				py::gil_scoped_release release;
-				out.data_ = llo::eval_device(tens, ctype);
-				out.data_.fetch_async();
-			}
+			out.data_ = llo::eval_device(tens, ctype);
+			out.data_.fetch_async();
 			return out;
 		}, "queue the evaluation and the copy of its result to pinned host "
 			"memory; .result() waits.  With Variable.assign_async the upload of "
@@ -432,20 +455,14 @@ PYBIND11_MODULE(_C, m)
 		{
 			age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);
 			pyllo::DeviceResult out;
-			{
-				py::gil_scoped_release release;
-				out.data_ = llo::eval_device(tens, ctype);
-			}
+			out.data_ = llo::eval_device(tens, ctype);
 			return out;
 		}, py::arg("tens"), py::arg("dtype") = py::dtype::of<double>());
 	llo_m.def("evaluate_device_many", [](std::vector<T> roots, py::dtype dtype)
 		{
 			age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);
 			std::vector<llo::GenericData> datas;
-			{
-				py::gil_scoped_release release;
-				datas = llo::eval_device_many(roots, ctype);
-			}
+			datas = llo::eval_device_many(roots, ctype);
 			std::vector<pyllo::DeviceResult> outs;
 			for (llo::GenericData& d : datas)
 			{
@@ -504,7 +521,6 @@ PYBIND11_MODULE(_C, m)
 				age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);
 				age::_GENERATED_OPCODE code = age::get_op(opname);
 				size_t count = self.nbytes_ / (size_t) dtype.itemsize();
-				py::gil_scoped_release release;
 				llo::device::check(llo_cuda_allreduce(llo::device::ctx(),
 					self.data_.get(), count, (int) ctype, (int) code,
 					ordered ? LLO_ALLREDUCE_ORDERED : LLO_ALLREDUCE_FAST));

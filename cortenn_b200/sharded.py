@@ -153,7 +153,8 @@ class BatchShardedExecutor:
         grads = ex.grad_eval(loss, params, np.float32)       # list of numpy arrays, summed over ranks
     """
 
-    def __init__(self, batch, rank=None, world=None, backend=None, exchange=None, ordered=False):
+    def __init__(self, batch, rank=None, world=None, backend=None, exchange=None, ordered=False,
+                 passes=None):
         self.rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
         self.world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else int(world)
         self.plan = ShardPlan(batch, self.world)
@@ -161,6 +162,13 @@ class BatchShardedExecutor:
         self.backend = backend if backend is not None else DeviceBackend(ordered=ordered)
         self.backend.init_comm(self.rank, self.world, exchange or _default_exchange)
         self._derived = {}
+        # graph -> graph passes applied to the derived gradients before they are
+        # evaluated (llo.optimize; None = llo.OPT_ALL, 0 = evaluate as derived).
+        # OPT_DIV_CANCEL is what turns the product rule's (a*b)/a into b, i.e. what
+        # lets the matmul gradients lower to GEMMs at all; it is inexact by <= 1 ulp
+        # per term and is named here, not hidden in the evaluator.
+        self.passes = passes
+        self.opt_report = None
 
     def shard(self, array):
         return np.ascontiguousarray(self.plan.slice(np.asarray(array), self.rank))
@@ -173,7 +181,15 @@ class BatchShardedExecutor:
         from . import llo
         key = (id(loss), tuple(id(p) for p in params))
         if key not in self._derived:
-            self._derived[key] = (loss, list(params), [llo.derive(loss, p) for p in params])
+            grads = [llo.derive(loss, p) for p in params]
+            passes = llo.OPT_ALL if self.passes is None else int(self.passes)
+            if passes:
+                # the loss is rewritten with the gradients so they keep sharing the forward pass
+                out, self.opt_report = llo.optimize([loss] + grads, passes)
+                opt_loss, grads = out[0], list(out[1:])
+            else:
+                opt_loss = loss
+            self._derived[key] = (loss, list(params), grads, opt_loss)
         return self._derived[key][2]
 
     def grad_eval_device(self, loss, params, dtype, with_loss=False):
@@ -182,7 +198,8 @@ class BatchShardedExecutor:
         roots = list(self.derive(loss, params))
         shapes = [self._shape(p) for p in params]
         if with_loss:
-            roots = [loss] + roots
+            key = (id(loss), tuple(id(p) for p in params))
+            roots = [self._derived[key][3]] + roots
             shapes = [()] + shapes
         pack = GradientPack(shapes, dtype)
         results = self.backend.evaluate_many(roots, dtype)

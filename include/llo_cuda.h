@@ -103,8 +103,9 @@ int llo_cuda_d2d (llo_cuda_ctx* ctx, void* dst, const void* src, size_t bytes);
  *   d2h_async: the copy starts once the work queued on the stream so far has
  *     finished and does not hold up later work; `*done` receives an event to
  *     pass to llo_cuda_event_sync (then llo_cuda_event_destroy).  `src` must
- *     stay allocated until then.  Device-side validation errors surface at
- *     the next llo_cuda_sync / llo_cuda_d2h, not here. */
+ *     stay allocated until then.  A device-side validation error raised by
+ *     the work before the copy is reported by that llo_cuda_event_sync (the
+ *     flag is snapshotted on the download lane right behind the copy). */
 int llo_cuda_h2d_async (llo_cuda_ctx* ctx, void* dst, const void* src_host, size_t bytes);
 int llo_cuda_d2h_async (llo_cuda_ctx* ctx, void* dst_host, const void* src, size_t bytes, void** done);
 int llo_cuda_event_sync (llo_cuda_ctx* ctx, void* event);
