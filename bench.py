@@ -12,12 +12,13 @@ inputs resident in HBM) and llo.evaluate with pinned host buffers (e2e).  A
 "step" is one evaluation of that graph.  Metric: algorithmic HBM GB/s =
 4 * (N + D + N) bytes / step time, whole job over all
 ranks.  With --gpus N > 1 every rank evaluates its own replica of the chain
-(the single-operator configs do not shard: "replicas only", weak scaling).
+(the single-operator configs do not shard: "replicas only", weak scaling); the
+workload that shards is the MLP gradient evaluation (`scaling_workload`).
 
-The other BASELINE.json configurations are reported under "workloads":
-reductions of [D, D] (config 3), matmul 8192^3 fp32 (config 4) and the
-batch-sharded MLP gradient evaluation with its NCCL allreduce (config 5, batch
-65536 split over the N ranks: strong scaling of that workload).
+The other BASELINE.json configurations are under "workloads", each with its own
+`roofline` block and a `verified` flag (the timed output is compared, outside
+the timed region, with float64 numpy at the full size), and once more, in a few
+hundred bytes, under "summary" at the very end of the line.
 
 One JSON line on stdout (rank 0).
 """
@@ -39,6 +40,7 @@ import workloads  # noqa: E402
 METRIC = "elementwise_chain_hbm_gbps"
 UNIT = "GB/s"
 F32 = np.dtype(np.float32)
+F64 = np.dtype(np.float64)
 
 
 def env_int(name, default):
@@ -53,17 +55,26 @@ def measured_peaks():
     if os.path.exists(path):
         with open(path) as fh:
             data = json.load(fh)
-        return float(data["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        return float(data["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ffma_peak():
-    """fp32 FFMA issue peak measured by tools/probes/fma_peak.cu on this pool"""
-    path = os.path.join(ROOT, "profiles", "fma_peak.json")
+def fma_peaks():
+    """FFMA / DFMA issue peaks: 148 SMs x 128 (64) lanes x 2 flop x the SM clock the
+    driver recorded (MEASURED_PEAKS.json sm_max_mhz); tools/probes/fma_peak.cu measured
+    72.5 / 37.0 TFLOP/s on this pool (profiles/fma_peak.json), 97 % of that product"""
+    mhz = 1965.0
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as fh:
-            return float(json.load(fh)["ffma_tflops"]), "measured (profiles/fma_peak.json)"
-    return 148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1965 MHz"
+            mhz = float(json.load(fh).get("sm_max_mhz", mhz))
+    nominal = 148 * 128 * 2 * mhz * 1e6 / 1e12
+    probe = os.path.join(ROOT, "profiles", "fma_peak.json")
+    if os.path.exists(probe):
+        with open(probe) as fh:
+            data = json.load(fh)
+        return float(data["ffma_tflops"]), float(data["dfma_tflops"]), "probe (profiles/fma_peak.json)", nominal
+    return nominal, nominal / 2, "148 SM x 128 lanes x 2 x sm_max_mhz", nominal
 
 
 class ClockSampler:
@@ -154,30 +165,87 @@ def cpu_chain(side, repeats):
     return sec, workloads.chain_bytes(side) / sec / 1e9
 
 
-def cpu_config1(age, llo):
-    """BASELINE.json configs[0]: the reference's CPU-runnable unit graphs over float
-    [64,64] through the oracle (single thread): ns per output element, median of 10"""
+def cpu_worker(args):
+    """one of the `nproc` independent oracle processes of the all-core figure"""
+    side = 1 << (args.cpu_log2n // 2)
+    sec, gbps = cpu_chain(side, max(1, args.cpu_repeats))
+    print(json.dumps({"sec": sec, "gbps": gbps}), flush=True)
+
+
+def cpu_all_cores(args):
+    """the reference has no threading, so the all-core figure is
+    `nproc` independent single-threaded oracle processes, each on the same chain sample"""
+    procs = os.cpu_count() or 1
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", "--cpu-log2n", str(args.cpu_log2n),
+           "--cpu-repeats", "2"]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    t0 = time.perf_counter()
+    running = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env, text=True)
+               for _ in range(procs)]
+    rates = []
+    for p in running:
+        try:
+            out, _ = p.communicate(timeout=180)
+            rates.append(json.loads(out.strip().splitlines()[-1])["gbps"])
+        except Exception:
+            p.kill()
+    if not rates:
+        return None
+    return {"GBps": float(sum(rates)), "processes": len(rates), "wall_s": time.perf_counter() - t0}
+
+
+def cpu_side_baselines(age, llo):
+    """the oracle (one thread, like the reference) on bounded samples
+    of configs 1, 3, 4 and 5; extrapolations are linear in elements / flops and say so"""
     oracle = oracle_module()
+
+    def timed(root, dtype=F32, repeats=1):
+        best = None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            oracle.evaluate(root, dtype)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return best
+
+    out = {}
+    # config 1: the reference's CPU-runnable unit graphs, float [64,64]
     rng = np.random.default_rng(1)
     x = rng.uniform(0.5, 1.5, (64, 64)).astype(np.float32)
     y = rng.uniform(0.5, 1.5, (64, 64)).astype(np.float32)
     vx, vy = llo.variable(x, "x"), llo.variable(y, "y")
     graphs = {"add": age.add(vx, vy), "mul": age.mul(vx, vy), "exp": age.exp(vx),
-              "reduce_sum_dim1": age.reduce_sum(vx, 1), "reduce_sum_all": age.reduce_sum0(vx),
-              "matmul": age.matmul(vx, vy)}
-    out = {}
-    for name, root in graphs.items():
-        times = []
-        for _ in range(10):
-            t0 = time.perf_counter()
-            oracle.evaluate(root, F32)
-            times.append(time.perf_counter() - t0)
-        sec = float(np.median(times))
-        entry = {"us": sec * 1e6, "ns_per_input_elem": sec * 1e9 / 4096}
-        if name == "matmul":
-            entry["MFLOPs"] = 2.0 * 64 ** 3 / sec / 1e6
-        out[name] = entry
-    out["note"] = "oracle = CPU restatement of llo::Evaluator, 1 thread, ade shape [64,64] fp32"
+              "rsum1": age.reduce_sum(vx, 1), "rsum0": age.reduce_sum0(vx), "matmul": age.matmul(vx, vy)}
+    out["c1_us"] = {k: round(timed(r, repeats=10) * 1e6, 1) for k, r in graphs.items()}
+    # config 3: reductions on a 2^20 sample
+    side = 1024
+    xs = np.random.default_rng(4).uniform(0.0, 1.0, (side, side)).astype(np.float32)
+    vs = llo.variable(xs, "x")
+    red = {"cols": age.reduce_sum(vs, 1), "all": age.reduce_sum0(vs),
+           "rows": age.reduce_sum(age.permute(vs, [1, 0]), 1)}
+    out["c3_GBps"] = {k: round(4.0 * side * side / timed(r) / 1e9, 4) for k, r in red.items()}
+    out["c3_sample"] = "reduce_sum of [1024,1024] fp32 (2^20 of 2^28 elements)"
+    # config 4: materialised [M,N,C] matmul of the reference at 64^3 and 128^3
+    mm = {}
+    for m in (64, 128):
+        a = llo.variable(np.random.default_rng(5).uniform(-1, 1, (m, m)).astype(np.float32), "a")
+        b = llo.variable(np.random.default_rng(6).uniform(-1, 1, (m, m)).astype(np.float32), "b")
+        mm[str(m)] = round(2.0 * m ** 3 / timed(age.matmul(a, b)) / 1e6, 2)
+    out["c4_MFLOPs"] = mm
+    out["c4_note"] = "O(MNC) mapped elements: 8192^3 extrapolates to ~2.8e5 s and needs 5 x 2.2 TB"
+    # config 5: down-scaled MLP 16-32-32-10, batch 32, six derived gradients
+    sizes, batch = (16, 32, 32, 10), 32
+    X, Y, params = workloads.mlp_data(batch, sizes=sizes)
+    loss, pvars, _ = workloads.mlp_graph(age, llo, X, Y, params)
+    grads = [llo.derive(loss, p) for p in pvars]
+    t0 = time.perf_counter()
+    for g in grads:
+        oracle.evaluate(g, F32)
+    sec = time.perf_counter() - t0
+    flops = workloads.mlp_flops(batch, sizes)
+    out["c5"] = {"grad_evals_per_s": round(1.0 / sec, 3), "sample": "MLP 16-32-32-10, batch 32",
+                 "MFLOPs": round(flops / sec / 1e6, 3),
+                 "extrapolated_s_per_grad_eval_at_65536": round(workloads.mlp_flops(65536) / (flops / sec), 0)}
     return out
 
 
@@ -196,9 +264,8 @@ def run_reference(args, rank, world):
         oracle.evaluate(root, F32)
     per_step = (time.perf_counter() - t0) / args.steps
     value = workloads.chain_bytes(side) / per_step / 1e9
-    sample = ("the same chain on x=[%d,%d] (2^%d elements) per step; the reference's evaluator "
-              "is single-threaded by construction (no threads, SIMD or BLAS: SURVEY.md 2.2), so "
-              "one core is all it can use" % (side, side, args.ref_log2n))
+    sample = ("the same chain on x=[%d,%d] (2^%d elements) per step; 1 thread: the reference "
+              "evaluator has no threads, SIMD or BLAS (SURVEY.md 2.2)" % (side, side, args.ref_log2n))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -240,15 +307,19 @@ class Timer:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(self, fn, steps, warmup, finish=None):
+    def timed(self, fn, steps, warmup, finish=None, collective=True):
         """ms per step of `fn`, max over ranks; also returns the launches.
         `finish` (pipelined callers) completes whatever the last step left in
-        flight; it runs inside the timed region and after the warm-up"""
+        flight; it runs inside the timed region and after the warm-up.
+        collective=False: this rank alone (no barrier, no max over ranks)."""
         for _ in range(warmup):
             fn()
         if finish is not None:
             finish()
-        self.barrier()
+        if collective:
+            self.barrier()
+        else:
+            self.llo.sync()
         launches0 = self.llo.launch_count()
         self.ctx.record(self.start)
         for _ in range(steps):
@@ -257,152 +328,326 @@ class Timer:
             finish()
         self.ctx.record(self.stop)
         ms = self.ctx.elapsed_ms(self.start, self.stop)
-        self.barrier()
+        if collective:
+            self.barrier()
         launches = self.llo.launch_count() - launches0
-        return self.max_over_ranks(ms) / steps, launches
+        return (self.max_over_ranks(ms) if collective else ms) / steps, launches
+
+
+def hbm_block(nbytes, ms, kernel):
+    peak, _ = measured_peaks()
+    gbps = nbytes / ms / 1e6
+    return {"bound": "hbm", "achieved": round(gbps, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(gbps / peak, 4), "kernel": kernel}
+
+
+def chain_verify(got, x, b):
+    """max relative error of the chain's full output against float64 numpy"""
+    side = x.shape[0]
+    worst = 0.0
+    b64 = b.astype(np.float64)[None, :]
+    for lo in range(0, side, 2048):
+        hi = min(side, lo + 2048)
+        want = np.exp(x[lo:hi].astype(np.float64)) * b64 + x[:, lo:hi].T.astype(np.float64)
+        worst = max(worst, float((np.abs(got[lo:hi].astype(np.float64) - want) / np.abs(want)).max()))
+    return worst
+
+
+def mlp_reference(X, Y, params, batch):
+    """float64 gradients of the MLP loss and the sum |terms| bound of every element"""
+    X, Y = X.astype(np.float64), Y.astype(np.float64)
+    P = [p.astype(np.float64) for p in params]
+    hs = [X]
+    for i in range(len(P) // 2):
+        hs.append(1.0 / (1.0 + np.exp(-(hs[-1] @ P[2 * i] + P[2 * i + 1]))))
+    grads, bounds = [None] * len(P), [None] * len(P)
+    delta = 2.0 * (hs[-1] - Y) / batch
+    for i in reversed(range(len(P) // 2)):
+        dz = delta * hs[i + 1] * (1.0 - hs[i + 1])
+        grads[2 * i], bounds[2 * i] = hs[i].T @ dz, np.abs(hs[i]).T @ np.abs(dz)
+        grads[2 * i + 1], bounds[2 * i + 1] = dz.sum(axis=0), np.abs(dz).sum(axis=0)
+        delta = dz @ P[2 * i].T
+    return grads, bounds
+
+
+def traffic_probe(args):
+    """DRAM bytes of one launch of the headline kernel, measured now: one short ncu pass
+    (dram__bytes_read.sum + dram__bytes_write.sum) over tools/prof_cases.py --case chain,
+    which launches the same kernel on the same shapes.  Returns (bytes, source)."""
+    fallback = os.path.join(ROOT, "profiles", "chain_traffic.json")
+
+    def from_file(why):
+        if os.path.exists(fallback):
+            with open(fallback) as fh:
+                return json.load(fh).get("dram_bytes_per_launch"), "profiles/chain_traffic.json (%s)" % why
+        return None, why
+    if args.no_traffic_probe:
+        return from_file("probe disabled")
+    ncu = None
+    for cand in ("ncu", "/usr/local/cuda/bin/ncu"):
+        try:
+            subprocess.run([cand, "--version"], capture_output=True, timeout=20, check=True)
+            ncu = cand
+            break
+        except Exception:
+            continue
+    if ncu is None:
+        return from_file("ncu not available")
+    case = [sys.executable, os.path.join(ROOT, "tools", "prof_cases.py"), "--case", "chain",
+            "--log2n", str(args.log2n), "--iters", "2"]
+    try:
+        plain = subprocess.run(case, capture_output=True, timeout=120)
+        if plain.returncode != 0:
+            return from_file("probe case failed")
+        fd, log = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        subprocess.run([ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
+                        "-k", "regex:vm_pair4", "-s", "1", "-c", "1", "--csv", "--log-file", log] + case,
+                       capture_output=True, timeout=180)
+        total = 0.0
+        import csv
+        with open(log) as fh:
+            rows = [r for r in csv.reader(fh) if len(r) > 5]
+        os.unlink(log)
+        hdr = rows[0]
+        i_name, i_unit, i_val = hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        seen = 0
+        for r in rows[1:]:
+            if r[i_name].startswith("dram__bytes_"):
+                total += float(r[i_val].replace(",", "")) * scale.get(r[i_unit], 1.0)
+                seen += 1
+        if seen < 2:
+            return from_file("ncu returned no dram metrics")
+        return total, "ncu dram__bytes_read.sum + dram__bytes_write.sum, measured in this run"
+    except Exception as exc:  # noqa: BLE001
+        return from_file("probe error: %s" % type(exc).__name__)
 
 
 def side_workloads(args, timer, age, llo, rank, world):
-    """BASELINE.json configs 3-5 (reported beside the headline)"""
+    """BASELINE.json configs 2 (per operator), 3, 4, 5"""
     out = {}
-    hbm_peak, _ = measured_peaks()
     steps, warm = max(3, min(args.steps, 10)), 3
+    check = not args.skip_verify
     if world == 1 and not args.skip_side:
-        # config 3: reductions of [D, D], deterministic tree order
         side = 1 << (args.log2n // 2)
+        n = side * side
         x = np.random.default_rng(4).uniform(0.0, 1.0, (side, side)).astype(np.float32)
         vx = llo.variable(x, "x")
-        nbytes = 4 * side * side
+        x64 = x.astype(np.float64) if check else None
+        # config 3: reductions of [D, D], fixed tree order.  "cols" keeps the fastest dim
+        # (strided columns), "rows" = reduce(permute(x)) with the permute fused, "all" = scalar
         cases = {
-            "reduce_sum_cols": age.reduce_sum(vx, 1),                      # keeps the fastest dim
-            "reduce_max_cols": age.reduce_max(vx, 1),
-            "reduce_sum_all": age.reduce_sum0(vx),
-            "reduce_max_all": age.reduce_max0(vx),
-            "reduce_sum_rows": age.reduce_sum(age.permute(vx, [1, 0]), 1),  # contiguous rows, permute fused
-            "reduce_max_rows": age.reduce_max(age.permute(vx, [1, 0]), 1),
+            "reduce_sum_cols": (age.reduce_sum(vx, 1), "col_fold_kernel", lambda: x64.sum(axis=0)),
+            "reduce_max_cols": (age.reduce_max(vx, 1), "col_fold_kernel", lambda: x64.max(axis=0)),
+            "reduce_sum_all": (age.reduce_sum0(vx), "row_fold_kernel", lambda: np.array(x64.sum())),
+            "reduce_max_all": (age.reduce_max0(vx), "row_fold_kernel", lambda: np.array(x64.max())),
+            "reduce_sum_rows": (age.reduce_sum(age.permute(vx, [1, 0]), 1), "row_fold_kernel", lambda: x64.sum(axis=1)),
+            "reduce_max_rows": (age.reduce_max(age.permute(vx, [1, 0]), 1), "row_fold_kernel", lambda: x64.max(axis=1)),
         }
-        for name, root in cases.items():
-            ms, launches = timer.timed(lambda r=root: llo.evaluate_device(r, F32), steps, warm)
-            gbps = nbytes / ms / 1e6
-            out[name] = {"GBps": gbps, "ms": ms, "frac_of_measured_hbm": gbps / hbm_peak,
-                         "launches_per_eval": launches // steps}
-        del cases
-        # config 3, reference-representable shape: [128,128,128,128], reduce_*(x, 2)
-        x4 = x.reshape(128, 128, side * side // (128 * 128 * 128), 128) if side * side >= 128 ** 4 else None
+        for name, (root, kernel, ref) in cases.items():
+            holder = {}
+
+            def step(r=root):
+                holder["res"] = llo.evaluate_device(r, F32)
+            ms, launches = timer.timed(step, steps, warm)
+            entry = {"ms": round(ms, 4), "roofline": hbm_block(4 * n, ms, kernel), "launches": launches // steps}
+            if check:
+                want = ref()
+                got = holder["res"].numpy(F32).reshape(want.shape).astype(np.float64)
+                err = float((np.abs(got - want) / np.abs(want)).max())
+                entry["max_rel_err"] = err
+                entry["verified"] = bool(err <= 1e-6)
+            out[name] = entry
+        del cases, x64
+        x4 = x.reshape(128, 128, n // (128 ** 3), 128) if n >= 128 ** 4 else None
         if x4 is not None:
             vx4 = llo.variable(x4, "x4")
             for name, root in (("reduce_sum_128x4_dim2", age.reduce_sum(vx4, 2)),
                                ("reduce_max_128x4_dim2", age.reduce_max(vx4, 2))):
                 ms, launches = timer.timed(lambda r=root: llo.evaluate_device(r, F32), steps, warm)
-                gbps = nbytes / ms / 1e6
-                out[name] = {"GBps": gbps, "ms": ms, "frac_of_measured_hbm": gbps / hbm_peak,
-                             "launches_per_eval": launches // steps}
+                out[name] = {"ms": round(ms, 4), "roofline": hbm_block(4 * n, ms, "col_fold_kernel")}
             del vx4
         # config 2, every operator stand-alone (SURVEY.md 8d): algorithmic bytes =
         # 4 * (distinct input elements + output elements)
         y = np.random.default_rng(5).uniform(0.5, 2.0, (side, side)).astype(np.float32)
         bb = np.random.default_rng(3).uniform(0.5, 2.0, (side,)).astype(np.float32)
         vy, vbb = llo.variable(y, "y"), llo.variable(bb, "b")
-        n = side * side
         ops = {
             "exp": (age.exp(vx), 2 * n), "sin": (age.sin(vx), 2 * n), "sqrt": (age.sqrt(vx), 2 * n),
-            "abs": (age.abs(vx), 2 * n), "neg": (age.neg(vx), 2 * n), "log": (age.log(vx), 2 * n),
+            "abs": (age.abs(vx), 2 * n), "neg": (age.neg(vx), 2 * n), "log": (age.log(vy), 2 * n),
             "add": (age.add(vx, vy), 3 * n), "sub": (age.sub(vx, vy), 3 * n),
             "mul": (age.mul(vx, vy), 3 * n), "div": (age.div(vx, vy), 3 * n),
-            "pow": (age.pow(vx, vy), 3 * n), "lt": (age.lt(vx, vy), 3 * n), "eq": (age.eq(vx, vy), 3 * n),
+            "pow": (age.pow(vy, vx), 3 * n), "lt": (age.lt(vx, vy), 3 * n), "eq": (age.eq(vx, vy), 3 * n),
             "extend": (age.extend(vbb, 1, [side]), n + side),
             "mul_extend": (age.mul(vx, age.extend(vbb, 1, [side])), 2 * n + side),
             "permute": (age.permute(vx, [1, 0]), 2 * n),
         }
+        peak, _ = measured_peaks()
         elem = {}
         for name, (root, elems) in ops.items():
             ms, launches = timer.timed(lambda r=root: llo.evaluate_device(r, F32), steps, warm)
             gbps = 4.0 * elems / ms / 1e6
-            elem[name] = {"GBps": round(gbps, 1), "ms": round(ms, 4), "frac_of_measured_hbm": round(gbps / hbm_peak, 3)}
-        out["elementwise_ops"] = elem
+            elem[name] = [round(gbps, 1), round(gbps / peak, 3)]
+        out["elementwise_ops"] = {"GBps_and_frac_of_measured_hbm": elem,
+                                  "kernels": "vm_flat_kernel (permute: vm_tile4_kernel)"}
         del ops, vy, vbb, y
-        # config 2, reference-representable shape: the chain over [128,128,128,128]
         if x4 is not None:
             vx4 = llo.variable(x4, "x4")
             b4 = llo.variable(bb[:128].copy(), "b4")
             rest = list(x4.shape[:-1])[::-1]
             root = age.add(age.mul(age.exp(vx4), age.extend(b4, 1, rest)), age.permute(vx4, [1, 0, 2, 3]))
             ms, launches = timer.timed(lambda: llo.evaluate_device(root, F32), steps, warm)
-            gbps = 4.0 * (2 * n + 128) / ms / 1e6
-            out["chain_128x4"] = {"GBps": gbps, "ms": ms, "frac_of_measured_hbm": gbps / hbm_peak,
-                                  "launches_per_eval": launches // steps}
+            out["chain_128x4"] = {"ms": round(ms, 4), "roofline": hbm_block(4 * (2 * n + 128), ms, "vm_pair4_kernel")}
             del vx4, b4, root
         del vx, x, x4, bb
-        # config 4: matmul 8192^3 — fp32 on the FFMA pipe (exact path), fp64 on
+        # config 4: matmul 8192^3 — fp32 on the FFMA pipe (exact path, FFMA2 issue), fp64 on
         # the DFMA pipe, and the opt-in 3xTF32 tensor-core path (tcgen05)
         m = args.matmul
         gsteps = max(3, steps // 2)
-        fpeak, fsrc = ffma_peak()
-        dpeak = fpeak / 2.0
-        ppath = os.path.join(ROOT, "profiles", "fma_peak.json")
-        if os.path.exists(ppath):
-            with open(ppath) as fh:
-                dpeak = float(json.load(fh).get("dfma_tflops", dpeak))
-        for name, dt, option in (("matmul_f32", np.float32, 0), ("matmul_f32_3xtf32", np.float32, 1),
-                                 ("matmul_f64", np.float64, 0)):
+        fpeak, dpeak, fsrc, _ = fma_peaks()
+        for name, dt, option, kernel in (("matmul_f32", np.float32, 0, "sgemm_tma_kernel<0,0> (FFMA2)"),
+                                         ("matmul_f32_3xtf32", np.float32, 1, "tf32x3_kernel (tcgen05)"),
+                                         ("matmul_f64", np.float64, 0, "dgemm_tma_kernel")):
             a = np.random.default_rng(5).uniform(-1, 1, (m, m)).astype(dt)
             b = np.random.default_rng(6).uniform(-1, 1, (m, m)).astype(dt)
             va, vb = llo.variable(a, "a"), llo.variable(b, "b")
             root = age.matmul(va, vb)
+            holder = {}
+
+            def step():
+                holder["res"] = llo.evaluate_device(root, np.dtype(dt))
             llo.set_option("tf32x3", option)
             try:
-                ms, launches = timer.timed(lambda: llo.evaluate_device(root, np.dtype(dt)), gsteps, 2)
+                ms, launches = timer.timed(step, gsteps, 2)
             finally:
                 llo.set_option("tf32x3", 0)
             tf = 2.0 * m ** 3 / ms / 1e9
-            entry = {"TFLOPs": tf, "ms": ms, "mnk": [m, m, m], "launches_per_eval": launches // gsteps}
+            entry = {"ms": round(ms, 3), "mnk": [m, m, m], "launches": launches // gsteps}
             if option:
-                entry["path"] = ("opt-in: tcgen05.mma kind::tf32, 3 products per k, TMEM accumulators promoted "
-                                 "every 128 k (results within 1e-6 of sum|a||b|, not bit-identical to FFMA)")
-                entry["speedup_vs_exact"] = tf / out["matmul_f32"]["TFLOPs"]
-            elif dt == np.float32:
-                entry.update({"frac_of_ffma_peak": tf / fpeak, "ffma_peak_TFLOPs": fpeak, "peak_source": fsrc})
+                entry["TFLOPs_fp32_equivalent"] = round(tf, 2)
+                entry["speedup_vs_exact"] = round(tf / out["matmul_f32"]["roofline"]["achieved"], 2)
+                entry["kernel"] = kernel
             else:
-                entry.update({"frac_of_dfma_peak": tf / dpeak, "dfma_peak_TFLOPs": dpeak})
+                peak_tf = fpeak if dt == np.float32 else dpeak
+                entry["roofline"] = {"bound": "ffma" if dt == np.float32 else "dfma", "achieved": round(tf, 2),
+                                     "peak": peak_tf, "unit": "TFLOP/s", "frac": round(tf / peak_tf, 4),
+                                     "kernel": kernel, "peak_source": fsrc}
+            if check:
+                rows = np.random.default_rng(7).choice(m, 64, replace=False)
+                got = holder["res"].numpy(np.dtype(dt))[rows].astype(np.float64)
+                a64, b64 = a[rows].astype(np.float64), b.astype(np.float64)
+                err = float((np.abs(got - a64 @ b64) / (np.abs(a64) @ np.abs(b64))).max())
+                entry["max_err_over_sum_abs"] = err
+                entry["verified"] = bool(err <= (1e-6 if dt == np.float32 else 1e-12))
             out[name] = entry
-            del va, vb, a, b, root
+            del va, vb, a, b, root, holder
     if not args.skip_mlp:
-        # config 5: MLP gradient evaluation, batch sharded over the ranks
-        from cortenn_b200.sharded import BatchShardedExecutor
-        batch = args.mlp_batch
-        X, Y, params = workloads.mlp_data(batch)
-        ex = BatchShardedExecutor(batch, rank=rank, world=world)
-        loss, pvars, _ = workloads.mlp_graph(age, llo, ex.shard(X), ex.shard(Y), params, global_batch=batch)
-        del X, Y
-
-        def grad_eval():
-            ex.grad_eval_device(loss, pvars, F32)
-        ms, launches = timer.timed(grad_eval, steps, warm)
-        # host time to plan + enqueue one evaluation (no synchronisation): it
-        # must stay below the device time or the GPU starves
-        timer.barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            grad_eval()
-        host_ms = (time.perf_counter() - t0) * 1e3 / steps
-        timer.barrier()
-        flops = workloads.mlp_flops(batch)
-        peak, _ = ffma_peak()
-        llo.set_option("tf32x3", 1)
-        try:
-            ms_tc, _ = timer.timed(grad_eval, steps, warm)
-        finally:
-            llo.set_option("tf32x3", 0)
-        out["mlp_grad_eval_3xtf32"] = {"grad_evals_per_s": 1e3 / ms_tc, "ms": ms_tc,
-                                       "path": "opt-in tensor-core GEMMs (tf32x3 = 1); same graph, same allreduce"}
-        out["mlp_grad_eval"] = {
-            "grad_evals_per_s": 1e3 / ms, "ms": ms, "batch": batch, "rows_per_rank": ex.local_rows(),
-            "gemm_TFLOPs_all_ranks": flops / ms / 1e9,
-            "frac_of_ffma_peak": flops / ms / 1e9 / (peak * world),
-            "allreduce_bytes": 4 * 1863690, "launches_per_eval": launches // steps,
-            "host_enqueue_ms": host_ms,
-            "scaling": "strong (batch 65536 split over the ranks; NCCL allreduce of the packed gradients)"}
+        out.update(mlp_workload(args, timer, age, llo, rank, world, steps, warm, check))
     return out
+
+
+def mlp_workload(args, timer, age, llo, rank, world, steps, warm, check):
+    """config 5: MLP gradient evaluation, batch sharded over the ranks (strong scaling)"""
+    from cortenn_b200.sharded import BatchShardedExecutor
+    out = {}
+    batch = args.mlp_batch
+    X, Y, params = workloads.mlp_data(batch)
+    ex = BatchShardedExecutor(batch, rank=rank, world=world)
+    loss, pvars, _ = workloads.mlp_graph(age, llo, ex.shard(X), ex.shard(Y), params, global_batch=batch)
+    holder = {}
+
+    def grad_eval():
+        holder["buf"], holder["pack"] = ex.grad_eval_device(loss, pvars, F32)
+    ms, launches = timer.timed(grad_eval, steps, warm)
+    # host time to plan + enqueue one evaluation (no synchronisation): it
+    # must stay below the device time or the GPU starves
+    timer.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        grad_eval()
+    host_ms = (time.perf_counter() - t0) * 1e3 / steps
+    timer.barrier()
+    flops = workloads.mlp_flops(batch)
+    fpeak, _, fsrc, _ = fma_peaks()
+    entry = {
+        "ms": round(ms, 4), "grad_evals_per_s": round(1e3 / ms, 2), "batch": batch, "rows_per_rank": ex.local_rows(),
+        "roofline": {"bound": "ffma", "achieved": round(flops / ms / 1e9, 2), "peak": fpeak * world,
+                     "unit": "TFLOP/s (GEMM flops of one grad-eval, all ranks)",
+                     "frac": round(flops / ms / 1e9 / (fpeak * world), 4), "kernel": "sgemm_* (FFMA2) + vm_flat + folds"},
+        "allreduce_bytes": 4 * 1863690, "launches": launches // steps, "host_enqueue_ms": round(host_ms, 3),
+        "graph_passes": "llo.optimize(OPT_ALL) on [loss] + llo.derive(...) (div_cancel %d, shared %d, functors %d -> %d)"
+                        % (ex.opt_report["div_cancel"], ex.opt_report["shared"], ex.opt_report["functors_before"],
+                           ex.opt_report["functors_after"]),
+        "scaling": "strong"}
+    got = None
+    if check:
+        got = ex.backend.to_host(holder["buf"], holder["pack"])
+    if check and world == 1:
+        want, bounds = mlp_reference(X, Y, params, batch)
+        worst = max(float((np.abs(g.reshape(w.shape).astype(np.float64) - w) / bnd).max())
+                    for g, w, bnd in zip(got, want, bounds))
+        entry["max_err_over_sum_abs_terms"] = worst
+        entry["verified"] = bool(worst <= 2e-5)
+    if world > 1:
+        # the gradient the ranks agreed on against the single-GPU gradient of the whole batch,
+        # evaluated now by rank 0 alone on its own GPU (and timed: the N = 1 time of this run)
+        n1 = {"ms": None}
+        if rank == 0:
+            solo = BatchShardedExecutor(batch, rank=0, world=1, backend=ex.backend.solo())
+            loss1, pvars1, _ = workloads.mlp_graph(age, llo, X, Y, params, global_batch=batch)
+            solo_holder = {}
+
+            def solo_eval():
+                solo_holder["out"] = solo.grad_eval_device(loss1, pvars1, F32)
+            n1["ms"], _ = timer.timed(solo_eval, max(3, steps // 2), 2, collective=False)
+            if check:
+                ref = solo.backend.to_host(*solo_holder["out"])
+                worst = max(float(np.abs(g.astype(np.float64) - r.astype(np.float64)).max() /
+                                  max(float(np.abs(r).max()), 1e-30)) for g, r in zip(got, ref))
+                entry["grad_max_diff_vs_n1_over_max_abs"] = worst
+                entry["grad_matches_n1"] = bool(worst <= 2e-6)
+            del solo, loss1, pvars1, solo_holder
+        timer.barrier()
+        if rank == 0 and n1["ms"]:
+            entry["n1_ms_same_run"] = round(n1["ms"], 4)
+            entry["speedup_vs_n1_same_run"] = round(n1["ms"] / ms, 3)
+    out["mlp_grad_eval"] = entry
+    del X, Y
+    llo.set_option("tf32x3", 1)
+    try:
+        ms_tc, _ = timer.timed(grad_eval, steps, warm)
+    finally:
+        llo.set_option("tf32x3", 0)
+    out["mlp_grad_eval_3xtf32"] = {"ms": round(ms_tc, 4), "grad_evals_per_s": round(1e3 / ms_tc, 2),
+                                   "path": "opt-in tensor-core GEMMs (tf32x3 = 1); same graph, same allreduce"}
+    return out
+
+
+def summarise(side, value_frac, verified):
+    """configs 2-5 in a few hundred bytes, last in the line (the driver keeps the tail)"""
+    def rf(name):
+        e = side.get(name)
+        if not e:
+            return None
+        r = e.get("roofline", {})
+        return [r.get("achieved"), r.get("frac"), e.get("verified")]
+    s = {"c2_chain_frac_verified": [round(value_frac, 4), verified]}
+    c3 = {k.replace("reduce_", ""): rf(k) for k in side if k.startswith("reduce_") and "128x4" not in k}
+    if c3:
+        s["c3_reduce_GBps_frac_verified"] = c3
+    c4 = {k.replace("matmul_", ""): rf(k) for k in ("matmul_f32", "matmul_f64") if k in side}
+    if "matmul_f32_3xtf32" in side:
+        e = side["matmul_f32_3xtf32"]
+        c4["3xtf32"] = [e.get("TFLOPs_fp32_equivalent"), None, e.get("verified")]
+    if c4:
+        s["c4_matmul_TFLOPs_frac_verified"] = c4
+    m = side.get("mlp_grad_eval")
+    if m:
+        s["c5_mlp"] = {"ms": m["ms"], "evals_per_s": m["grad_evals_per_s"], "frac_ffma": m["roofline"]["frac"],
+                       "verified": m.get("verified"), "grad_matches_n1": m.get("grad_matches_n1"),
+                       "speedup_vs_n1": m.get("speedup_vs_n1_same_run")}
+    return s
 
 
 def run_own(args, rank, local_rank, world):
@@ -434,9 +679,19 @@ def run_own(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_step, launches = timer.timed(lambda: llo.evaluate_device(root, F32), args.steps, 0)
+    last = {}
+
+    def chain_step():
+        last["res"] = llo.evaluate_device(root, F32)
+    ms_step, launches = timer.timed(chain_step, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else {}
     value = world * nbytes / ms_step / 1e6
+    verified = None
+    chain_err = None
+    if rank == 0 and not args.skip_verify:
+        chain_err = chain_verify(last["res"].numpy(F32), x, b)
+        verified = bool(chain_err <= 1e-6)
+    last.clear()
 
     # ---- e2e: pinned host buffers in, host buffer out, copies inside the timed region --
     # Every step uploads its input (1 GiB) from pinned host memory, evaluates the graph and
@@ -476,8 +731,7 @@ def run_own(args, rank, local_rank, world):
     e2e = {"value": world * nbytes / e2e_ms / 1e6, "unit": UNIT,
            "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(out.nbytes),
            "steps": e2e_steps, "ms_per_step": e2e_ms,
-           "path": "Variable.assign_async(pinned ndarray) + llo.evaluate_async -> .result() ndarray, every "
-                   "step; upload of step i+1 overlaps the download of step i",
+           "path": "Variable.assign_async(pinned) + llo.evaluate_async -> .result(), pipelined",
            "pcie_GBps_each_way": (x.nbytes + out.nbytes) / 2 / e2e_ms / 1e6,
            "synchronous": {"value": world * nbytes / sync_ms / 1e6, "ms_per_step": sync_ms,
                            "path": "Variable.assign + llo.evaluate, copies back to back"}}
@@ -488,28 +742,27 @@ def run_own(args, rank, local_rank, world):
     roofline = {"bound": "hbm", "achieved": nbytes / ms_step / 1e6, "peak": peak, "unit": "GB/s",
                 "frac": nbytes / ms_step / 1e6 / peak, "traffic": None, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": nbytes / ms_step / 1e6 / 8000.0,
-                "kernel": "vm_pair4_kernel<float> (the whole step is %d launch per evaluation)" % per_eval,
+                "kernel": "vm_pair4_kernel<float> (%d launch per step)" % per_eval,
                 "algorithmic_bytes_per_launch": nbytes}
-    traffic_path = os.path.join(ROOT, "profiles", "chain_traffic.json")
-    if os.path.exists(traffic_path):
-        with open(traffic_path) as fh:
-            roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
 
     cpu_baseline = None
+    cpu_more = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cside = 1 << (args.cpu_log2n // 2)
         sec, gbps = cpu_chain(cside, args.cpu_repeats)
         cpu_baseline = {"value": gbps, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": "oracle (CPU restatement of llo::Evaluator) on the same chain at "
-                                  "x=[%d,%d] (2^%d of the 2^%d elements), %d evaluations of %.2f s, "
-                                  "single thread like the reference; host has %d cores"
-                                  % (cside, cside, args.cpu_log2n, args.log2n, args.cpu_repeats, sec,
-                                     os.cpu_count() or 0)}
+                        "sample": "oracle on the same chain at x=[%d,%d] (2^%d of 2^%d elements), %d x %.2f s, 1 thread "
+                                  "like the reference; host has %d cores"
+                                  % (cside, cside, args.cpu_log2n, args.log2n, args.cpu_repeats, sec, os.cpu_count() or 0)}
+        cpu_more = cpu_side_baselines(age, llo)
+        cpu_more["all_cores_chain"] = cpu_all_cores(args)
 
-    del vx, vb, root, x, b
+    del vx, vb, root
     side_results = side_workloads(args, timer, age, llo, rank, world)
-    if cpu_baseline is not None:
-        side_results["cpu_config1"] = cpu_config1(age, llo)
+    if rank == 0 and world == 1:
+        # after every timed region: one short ncu pass for the DRAM bytes of the headline kernel
+        roofline["traffic"], roofline["traffic_source"] = traffic_probe(args)
+    del x, b
 
     if rank == 0:
         line = {
@@ -517,16 +770,27 @@ def run_own(args, rank, local_rank, world):
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "elementwise chain add(mul(exp(x),extend(b,1,{D})),permute(x,{1,0})), "
-                                   "x=[%d,%d] fp32 (2^%d elements), ade graph via age API -> llo.evaluate_device"
-                                   % (side, side, args.log2n),
+            "config": {"workload": "chain add(mul(exp(x),extend(b,1,{D})),permute(x,{1,0})), x=[%d,%d] fp32, age graph -> "
+                                   "llo.evaluate_device" % (side, side),
                        "bytes_per_step": nbytes,
                        "l2": "inputs larger than L2 (x is %d MiB, L2 is 126 MB)" % ((4 * side * side) >> 20),
-                       "multi_gpu": "independent replicas per rank (single-operator configs do not shard); "
-                                    "the batch-sharded MLP is under workloads.mlp_grad_eval"},
+                       "multi_gpu": "replicas per rank (single-operator configs do not shard); see scaling_workload"},
+            "verified": verified, "max_rel_err_vs_float64": chain_err,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "workloads": side_results,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
+        if cpu_more is not None:
+            line["cpu_baselines"] = cpu_more
+        line["workloads"] = side_results
+        mlp = side_results.get("mlp_grad_eval")
+        if mlp is not None:
+            line["scaling_workload"] = {
+                "name": "mlp_grad_eval (MLP 784-1024-1024-10, batch %d split over the ranks, NCCL allreduce)" % args.mlp_batch,
+                "scaling": "strong", "n_gpus": world, "ms": mlp["ms"], "grad_evals_per_s": mlp["grad_evals_per_s"],
+                "n1_ms_same_run": mlp.get("n1_ms_same_run", mlp["ms"] if world == 1 else None),
+                "speedup_vs_n1_same_run": mlp.get("speedup_vs_n1_same_run", 1.0 if world == 1 else None),
+                "grad_matches_n1": mlp.get("grad_matches_n1", mlp.get("verified") if world == 1 else None)}
+        line["summary"] = summarise(side_results, roofline["frac"], verified)
         print(json.dumps(line), flush=True)
     if dist is not None:
         timer.barrier()
@@ -542,7 +806,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--log2n", type=int, default=28, help="elements of the chain (2^k, k even)")
     ap.add_argument("--cpu-log2n", type=int, default=22, help="elements of the CPU-baseline sample")
-    ap.add_argument("--cpu-repeats", type=int, default=10)
+    ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--ref-log2n", type=int, default=20, help="elements per step of the reference arm")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--matmul", type=int, default=8192)
@@ -550,7 +814,13 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-side", action="store_true", help="skip the reduce / matmul workloads")
     ap.add_argument("--skip-mlp", action="store_true")
+    ap.add_argument("--skip-verify", action="store_true", help="do not compare the timed outputs with float64 numpy")
+    ap.add_argument("--no-traffic-probe", action="store_true", help="do not run the ncu DRAM-bytes pass")
+    ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_worker:
+        cpu_worker(args)
+        return
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
     world = env_int("WORLD_SIZE", 1)

@@ -1344,7 +1344,9 @@ static int launch_tile (llo_cuda_ctx* ctx, VmParams& p, int nstaged,
 			// persistent: an even CTA count keeps mirror pairs side by side
 			blocks = cap;
 		}
-		if (smem > 48 * 1024)
+		// (static shared memory counts against the 48 KB default too, so the
+		// opt-in is taken from 32 KB of dynamic memory on)
+		if (smem > 32 * 1024)
 		{
 			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_tile4_kernel<T,true>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -1374,13 +1376,19 @@ static int launch_tile (llo_cuda_ctx* ctx, VmParams& p, int nstaged,
 		{
 			vm_tile4_kernel<T,false><<<blocks, VM_THREADS, smem, ctx->stream>>>(p);
 		}
-		return launched(ctx, "vm_tile4_kernel");
+		if (LLO_OK != launched(ctx, "vm_tile4_kernel"))
+		{
+			std::string why = llo_cuda_last_error();
+			return fail(LLO_ERR_CUDA, "%s (blocks %u, smem %zu, staged %d, spill %zu)",
+				why.c_str(), blocks, smem, nstaged, spill);
+		}
+		return LLO_OK;
 	}
 	else
 	{
 		size_t smem = (size_t) VM_MAX_TILE_INPUTS * G::TILEP * G::PITCH *
 			sizeof(T) + spill;
-		if (smem > 48 * 1024)
+		if (smem > 32 * 1024)
 		{
 			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_tile_kernel<T>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -1425,7 +1433,7 @@ int vm_launch (llo_cuda_ctx* ctx, int dtype, void* out,
 		{
 			return fail(LLO_ERR_FATAL, "elementwise launch too large");
 		}
-		if (spill > 48 * 1024)
+		if (spill > 32 * 1024)
 		{
 			LLO_CUDA_TRY(cudaFuncSetAttribute(vm_flat_kernel<T>,
 				cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

@@ -127,11 +127,33 @@ class DeviceBackend:
         buf.allreduce(pack.dtype, "SUM", self.ordered)
         return buf
 
+    def solo(self):
+        return SoloDeviceBackend()
+
     def to_host(self, buf, pack):
         return pack.unpack(buf.numpy(pack.dtype, 0, pack.count))
 
     def scalar(self, buf, pack, index):
         return buf.numpy(pack.dtype, pack.offsets[index] * pack.dtype.itemsize, 1)[0]
+
+
+class SoloDeviceBackend(DeviceBackend):
+    """This rank alone on its own GPU, leaving the ranks' communicator untouched: the
+    single-GPU evaluation a multi-rank run checks its agreed gradient against"""
+
+    def init_comm(self, rank, world, exchange):
+        if world != 1:
+            raise ValueError("the solo backend evaluates on one rank")
+
+    def reduce_packed(self, results, pack):
+        buf = self._buffers.get(pack.nbytes)
+        if buf is None:
+            buf = self.llo.DeviceBuffer(pack.nbytes)
+            self._buffers[pack.nbytes] = buf
+        itemsize = pack.dtype.itemsize
+        for off, res in zip(pack.offsets, results):
+            buf.store(off * itemsize, res)
+        return buf
 
 
 def _default_exchange(ident):

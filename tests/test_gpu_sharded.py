@@ -29,7 +29,7 @@ def gpu_count():
 def test_evaluate_many_shares_the_forward_pass():
     X, Y, params = workloads.mlp_data(32, (20, 24, 16, 6), F4)
     loss, pvars, _ = workloads.mlp_graph(age, llo, X, Y, params)
-    roots = [loss] + [llo.derive(loss, p) for p in pvars]
+    roots, _ = llo.optimize([loss] + [llo.derive(loss, p) for p in pvars])   # as the executor does
     llo.sync()
     before = llo.launch_count()
     singles = [llo.evaluate(r, np.dtype(F4)) for r in roots]
