@@ -81,6 +81,8 @@ EXPORTS = {
     "llo_cuda_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
     "llo_cuda_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     "llo_cuda_event_destroy": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "llo_cuda_set_specialize_min": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "llo_cuda_specialize_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "llo_cuda_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint64]),
     "llo_cuda_unary": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(Arg)]),
     "llo_cuda_binary": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(Arg), C.POINTER(Arg)]),

@@ -57,6 +57,13 @@ struct llo_cuda_ctx
 	void* comm = nullptr;
 	int comm_rank = 0;
 	int comm_size = 1;
+	// run-time specialisation of the elementwise engine (specialize.cu):
+	// launches of at least spec_min output elements use the NVRTC build
+	uint64_t spec_min = 1ull << 20;
+	uint64_t spec_launches = 0;   // launches that ran a specialised kernel
+	uint64_t spec_compiles = 0;   // NVRTC compilations (cache misses)
+	uint64_t spec_disk_hits = 0;  // cubins taken from the on-disk cache
+	uint64_t spec_failures = 0;   // builds that failed (interpreted kernel ran)
 };
 
 namespace llo_cuda

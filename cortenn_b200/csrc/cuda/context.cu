@@ -4,6 +4,8 @@
 /// store (llo/src/data.cpp:8-18).
 ///
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace llo_cuda
@@ -110,6 +112,10 @@ int llo_cuda_init (int device, llo_cuda_ctx** out)
 		return fail_cuda(err, "cudaMalloc(error flag)");
 	}
 	cudaMemset(ctx->dev_error, 0, 4 * sizeof(int));
+	if (const char* env = std::getenv("LLO_SPECIALIZE_MIN"))
+	{
+		ctx->spec_min = std::strtoull(env, nullptr, 10);
+	}
 	*out = ctx;
 	return LLO_OK;
 }

@@ -32,7 +32,9 @@
 #ifndef LLO_CUDA_VM_CUH
 #define LLO_CUDA_VM_CUH
 
+#ifndef __CUDACC_RTC__
 #include "common.cuh"
+#endif
 #include "ops.cuh"
 
 namespace llo_cuda
@@ -65,6 +67,7 @@ struct FastDiv
 	uint32_t s;
 };
 
+#ifndef __CUDACC_RTC__
 /// n / d for n < 2^31 with one multiply-high
 inline FastDiv make_fastdiv (uint32_t d)
 {
@@ -79,6 +82,7 @@ inline FastDiv make_fastdiv (uint32_t d)
 	f.m = (uint32_t) (((1ull << 32) * ((1ull << s) - d)) / d + 1);
 	return f;
 }
+#endif
 
 __device__ __forceinline__ uint32_t fastdiv (uint32_t n, const FastDiv& f)
 {
@@ -168,6 +172,38 @@ struct VmParams
 	VmOp code[VM_MAX_CODE];
 };
 
+/// What a loader branches on for one input.  In the interpreted build these
+/// are read from VmParams at run time (warp-uniform branches); in the
+/// specialised build (LLO_VM_STATIC, NVRTC) they are compile-time constants
+/// and the branches fold away.  s0 / s1: the stride along output dim 0 / 1
+/// as a class -- 0 (broadcast), 1 (contiguous) or 2 (anything else).
+struct VmKind
+{
+	int mode;
+	int s0;
+	int s1;
+	int vec_ok;
+};
+
+__device__ __forceinline__ int vm_stride_class (int64_t stride)
+{
+	return 0 == stride ? 0 : (1 == stride ? 1 : 2);
+}
+
+__device__ __forceinline__ VmKind vm_kind (const VmParams& p, int k)
+{
+	const VmInput& in = p.in[k];
+	return VmKind{in.mode, vm_stride_class(in.stride[0]),
+		vm_stride_class(in.stride[1]), in.vec_ok};
+}
+
+#ifdef LLO_VM_STATIC
+// the specialised build knows the collapsed rank when it is 2 or 3 (0 = any)
+#define LLO_VM_NDIMS(p) (LLO_VM_STATIC_NDIMS > 0 ? LLO_VM_STATIC_NDIMS : (p).ndims)
+#else
+#define LLO_VM_NDIMS(p) ((p).ndims)
+#endif
+
 /// E elements from `src`: one 128-bit load when aligned and complete, scalar
 /// loads otherwise.  STREAM marks data read exactly once (evict-first);
 /// views that revisit elements (broadcasts) keep the default policy so they
@@ -236,7 +272,7 @@ __device__ __forceinline__ int64_t strided_offset (const VmParams& p,
 	{
 		uint32_t rem = (uint32_t) i;
 		int32_t off = (int32_t) in.offset;
-		int last = p.ndims - 1;
+		int last = LLO_VM_NDIMS(p) - 1;
 		for (int d = 0; d < last; ++d)
 		{
 			uint32_t q = fastdiv(rem, p.div[d]);
@@ -263,15 +299,15 @@ __device__ __forceinline__ int64_t strided_offset (const VmParams& p,
 /// along output dim 0
 template <typename T, int E>
 __device__ __forceinline__ void load_strided_chunk (T* dst,
-	const VmInput& in, int64_t off, int valid)
+	const VmInput& in, const VmKind& kind, int64_t off, int valid)
 {
 	const T* data = static_cast<const T*>(in.data);
 	int64_t s0 = in.stride[0];
-	if (1 == s0)
+	if (1 == kind.s0)
 	{
-		load_chunk<T,E,false>(dst, data + off, in.vec_ok, valid);
+		load_chunk<T,E,false>(dst, data + off, kind.vec_ok, valid);
 	}
-	else if (0 == s0)
+	else if (0 == kind.s0)
 	{
 		T v = __ldg(data + off);
 #pragma unroll
@@ -338,21 +374,22 @@ struct FlatLoader
 		return left < (uint64_t) G::E ? (int) left : G::E;
 	}
 
-	__device__ __forceinline__ void load (T (&x)[G::V], int k) const
+	__device__ __forceinline__ void load (T (&x)[G::V], int k,
+		const VmKind& kind) const
 	{
 		const VmInput& in = p.in[k];
 		const T* data = static_cast<const T*>(in.data);
-		if (VM_IN_LINEAR == in.mode)
+		if (VM_IN_LINEAR == kind.mode)
 		{
 			const T* src = data + in.offset + first(0);
 #pragma unroll
 			for (int u = 0; u < G::U; ++u)
 			{
 				load_chunk<T,G::E,true>(x + u * G::E,
-					src + u * VM_THREADS * G::E, in.vec_ok, valid(u));
+					src + u * VM_THREADS * G::E, kind.vec_ok, valid(u));
 			}
 		}
-		else if (VM_IN_INDEXED == in.mode)
+		else if (VM_IN_INDEXED == kind.mode)
 		{
 #pragma unroll
 			for (int u = 0; u < G::U; ++u)
@@ -375,7 +412,7 @@ struct FlatLoader
 #pragma unroll
 			for (int u = 0; u < G::U; ++u)
 			{
-				load_strided_chunk<T,G::E>(x + u * G::E, in, off + u * step,
+				load_strided_chunk<T,G::E>(x + u * G::E, in, kind, off + u * step,
 					G::E);
 			}
 		}
@@ -387,7 +424,7 @@ struct FlatLoader
 			{
 				int ok = valid(u);
 				int64_t off = ok > 0 ? strided_offset(p, in, first(u)) : in.offset;
-				load_strided_chunk<T,G::E>(x + u * G::E, in, off, ok);
+				load_strided_chunk<T,G::E>(x + u * G::E, in, kind, off, ok);
 			}
 		}
 		else
@@ -480,6 +517,99 @@ __device__ __noinline__ VmQuad<T> vm_outlined (VmQuad<T> acc, VmQuad<T> x)
 		LLO_VM_EACH(acc[e] = (vm_bulky<SEL,T>(acc[e], acc[e])))\
 	}
 
+/// acc <- f(acc, x) for one accumulator-form operation (PUSH / POP are the
+/// caller's business)
+template <int SEL, typename T, bool COMPACT>
+__device__ __forceinline__ void vm_apply (T (&acc)[VmGeom<T>::V],
+	T (&x)[VmGeom<T>::V])
+{
+	constexpr int V = VmGeom<T>::V;
+	if constexpr (VM_S_SET == SEL) { LLO_VM_EACH(acc[e] = x[e]) }
+	else if constexpr (VM_S_ABS == SEL) { LLO_VM_EACH(acc[e] = m_abs(acc[e])) }
+	else if constexpr (VM_S_NEG == SEL) { LLO_VM_EACH(acc[e] = m_neg(acc[e])) }
+	else if constexpr (VM_S_ROUND == SEL) { LLO_VM_BULKY(VM_S_ROUND) }
+	else if constexpr (VM_S_SIN == SEL) { LLO_VM_BULKY(VM_S_SIN) }
+	else if constexpr (VM_S_COS == SEL) { LLO_VM_BULKY(VM_S_COS) }
+	else if constexpr (VM_S_TAN == SEL) { LLO_VM_BULKY(VM_S_TAN) }
+	else if constexpr (VM_S_EXP == SEL) { LLO_VM_EACH(acc[e] = m_exp(acc[e])) }
+	else if constexpr (VM_S_LOG == SEL) { LLO_VM_BULKY(VM_S_LOG) }
+	else if constexpr (VM_S_SQRT == SEL) { LLO_VM_BULKY(VM_S_SQRT) }
+	else if constexpr (VM_S_SUM == SEL) { LLO_VM_EACH(acc[e] = m_add(acc[e], x[e])) }
+	else if constexpr (VM_S_PROD == SEL) { LLO_VM_EACH(acc[e] = m_mul(acc[e], x[e])) }
+	else if constexpr (VM_S_SUB == SEL) { LLO_VM_EACH(acc[e] = m_sub(acc[e], x[e])) }
+	else if constexpr (VM_S_RSUB == SEL) { LLO_VM_EACH(acc[e] = m_sub(x[e], acc[e])) }
+	else if constexpr (VM_S_MIN == SEL) { LLO_VM_EACH(acc[e] = m_min(acc[e], x[e])) }
+	else if constexpr (VM_S_RMIN == SEL) { LLO_VM_EACH(acc[e] = m_min(x[e], acc[e])) }
+	else if constexpr (VM_S_MAX == SEL) { LLO_VM_EACH(acc[e] = m_max(acc[e], x[e])) }
+	else if constexpr (VM_S_RMAX == SEL) { LLO_VM_EACH(acc[e] = m_max(x[e], acc[e])) }
+	else if constexpr (VM_S_EQ == SEL) { LLO_VM_EACH(acc[e] = (T) (acc[e] == x[e])) }
+	else if constexpr (VM_S_NEQ == SEL) { LLO_VM_EACH(acc[e] = (T) (acc[e] != x[e])) }
+	else if constexpr (VM_S_LT == SEL) { LLO_VM_EACH(acc[e] = (T) (acc[e] < x[e])) }
+	else if constexpr (VM_S_GT == SEL) { LLO_VM_EACH(acc[e] = (T) (acc[e] > x[e])) }
+	else if constexpr (VM_S_DIV == SEL) { LLO_VM_BULKY(VM_S_DIV) }
+	else if constexpr (VM_S_RDIV == SEL) { LLO_VM_BULKY(VM_S_RDIV) }
+	else if constexpr (VM_S_POW == SEL) { LLO_VM_BULKY(VM_S_POW) }
+	else if constexpr (VM_S_RPOW == SEL) { LLO_VM_BULKY(VM_S_RPOW) }
+}
+
+#ifdef LLO_VM_STATIC
+
+/// Specialised build: instruction PC of the compile-time program
+/// (LLO_VM_S_SEL / LLO_VM_S_ARG and the per-input kind tables are emitted by
+/// specialize.cu in front of this file).  Straight-line code: no dispatch, no
+/// accumulator copies, operand-kind branches resolved, the spill depth a
+/// template argument.
+template <int PC, int DEPTH, typename T, typename Loader>
+__device__ __forceinline__ void vm_step (T (&acc)[VmGeom<T>::V],
+	const VmParams& p, const Loader& loader, T* spill)
+{
+	if constexpr (PC < LLO_VM_S_NINSNS)
+	{
+		constexpr int V = VmGeom<T>::V;
+		constexpr int sel = LLO_VM_S_SEL[PC];
+		constexpr int arg = LLO_VM_S_ARG[PC];
+		constexpr int src = arg >> 4;
+		constexpr int k = arg & 15;
+		T x[V];
+		if constexpr (VM_SRC_IN == src)
+		{
+			loader.load(x, k, VmKind{LLO_VM_S_MODE[k], LLO_VM_S_S0[k],
+				LLO_VM_S_S1[k], LLO_VM_S_VEC[k]});
+		}
+		else if constexpr (VM_SRC_CONST == src)
+		{
+			T c;
+			memcpy(&c, &p.consts[k], sizeof(T));
+			LLO_VM_EACH(x[e] = c)
+		}
+		else if constexpr (VM_SRC_POP == src)
+		{
+			const T* sp = spill + (size_t) (DEPTH - 1) * V * VM_THREADS + threadIdx.x;
+			LLO_VM_EACH(x[e] = sp[e * VM_THREADS])
+		}
+		if constexpr (VM_S_PUSH == sel)
+		{
+			T* sp = spill + (size_t) DEPTH * V * VM_THREADS + threadIdx.x;
+			LLO_VM_EACH(sp[e * VM_THREADS] = acc[e])
+		}
+		else
+		{
+			vm_apply<sel,T,false>(acc, x);
+		}
+		vm_step<PC + 1, DEPTH + (VM_S_PUSH == sel ? 1 : 0) -
+			(VM_SRC_POP == src ? 1 : 0), T, Loader>(acc, p, loader, spill);
+	}
+}
+
+template <typename T, typename Loader, bool COMPACT = false>
+__device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
+	const VmParams& p, const Loader& loader, T* spill)
+{
+	vm_step<0, 0, T, Loader>(acc, p, loader, spill);
+}
+
+#else // interpreted
+
 /// Run the accumulator program for this thread's V outputs.  `spill` is the
 /// CTA's shared-memory spill area ([level][element][thread]).
 template <typename T, typename Loader, bool COMPACT = false>
@@ -494,7 +624,7 @@ __device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
 		int arg = p.code[0].arg;
 		if (VM_SRC_IN == (arg >> 4))
 		{
-			loader.load(acc, arg & 15);
+			loader.load(acc, arg & 15, vm_kind(p, arg & 15));
 		}
 		else
 		{
@@ -512,7 +642,7 @@ __device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
 		T x[V];
 		if (VM_SRC_IN == src)
 		{
-			loader.load(x, arg & 15);
+			loader.load(x, arg & 15, vm_kind(p, arg & 15));
 		}
 		else if (VM_SRC_CONST == src)
 		{
@@ -528,7 +658,6 @@ __device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
 		}
 		switch (sel)
 		{
-			case VM_S_SET: LLO_VM_EACH(acc[e] = x[e]) break;
 			case VM_S_PUSH:
 			{
 				T* sp = spill + (size_t) depth * V * VM_THREADS + threadIdx.x;
@@ -536,36 +665,25 @@ __device__ __forceinline__ void vm_exec (T (&acc)[VmGeom<T>::V],
 				++depth;
 			}
 				break;
-			case VM_S_ABS: LLO_VM_EACH(acc[e] = m_abs(acc[e])) break;
-			case VM_S_NEG: LLO_VM_EACH(acc[e] = m_neg(acc[e])) break;
-			case VM_S_ROUND: LLO_VM_BULKY(VM_S_ROUND) break;
-			case VM_S_SIN: LLO_VM_BULKY(VM_S_SIN) break;
-			case VM_S_COS: LLO_VM_BULKY(VM_S_COS) break;
-			case VM_S_TAN: LLO_VM_BULKY(VM_S_TAN) break;
-			case VM_S_EXP: LLO_VM_EACH(acc[e] = m_exp(acc[e])) break;
-			case VM_S_LOG: LLO_VM_BULKY(VM_S_LOG) break;
-			case VM_S_SQRT: LLO_VM_BULKY(VM_S_SQRT) break;
-			case VM_S_SUM: LLO_VM_EACH(acc[e] = m_add(acc[e], x[e])) break;
-			case VM_S_PROD: LLO_VM_EACH(acc[e] = m_mul(acc[e], x[e])) break;
-			case VM_S_SUB: LLO_VM_EACH(acc[e] = m_sub(acc[e], x[e])) break;
-			case VM_S_RSUB: LLO_VM_EACH(acc[e] = m_sub(x[e], acc[e])) break;
-			case VM_S_MIN: LLO_VM_EACH(acc[e] = m_min(acc[e], x[e])) break;
-			case VM_S_RMIN: LLO_VM_EACH(acc[e] = m_min(x[e], acc[e])) break;
-			case VM_S_MAX: LLO_VM_EACH(acc[e] = m_max(acc[e], x[e])) break;
-			case VM_S_RMAX: LLO_VM_EACH(acc[e] = m_max(x[e], acc[e])) break;
-			case VM_S_EQ: LLO_VM_EACH(acc[e] = (T) (acc[e] == x[e])) break;
-			case VM_S_NEQ: LLO_VM_EACH(acc[e] = (T) (acc[e] != x[e])) break;
-			case VM_S_LT: LLO_VM_EACH(acc[e] = (T) (acc[e] < x[e])) break;
-			case VM_S_GT: LLO_VM_EACH(acc[e] = (T) (acc[e] > x[e])) break;
-			case VM_S_DIV: LLO_VM_BULKY(VM_S_DIV) break;
-			case VM_S_RDIV: LLO_VM_BULKY(VM_S_RDIV) break;
-			case VM_S_POW: LLO_VM_BULKY(VM_S_POW) break;
-			case VM_S_RPOW: LLO_VM_BULKY(VM_S_RPOW) break;
+#define LLO_VM_CASE(SEL) case SEL: vm_apply<SEL,T,COMPACT>(acc, x); break;
+			LLO_VM_CASE(VM_S_SET) LLO_VM_CASE(VM_S_ABS) LLO_VM_CASE(VM_S_NEG)
+			LLO_VM_CASE(VM_S_ROUND) LLO_VM_CASE(VM_S_SIN) LLO_VM_CASE(VM_S_COS)
+			LLO_VM_CASE(VM_S_TAN) LLO_VM_CASE(VM_S_EXP) LLO_VM_CASE(VM_S_LOG)
+			LLO_VM_CASE(VM_S_SQRT) LLO_VM_CASE(VM_S_SUM) LLO_VM_CASE(VM_S_PROD)
+			LLO_VM_CASE(VM_S_SUB) LLO_VM_CASE(VM_S_RSUB) LLO_VM_CASE(VM_S_MIN)
+			LLO_VM_CASE(VM_S_RMIN) LLO_VM_CASE(VM_S_MAX) LLO_VM_CASE(VM_S_RMAX)
+			LLO_VM_CASE(VM_S_EQ) LLO_VM_CASE(VM_S_NEQ) LLO_VM_CASE(VM_S_LT)
+			LLO_VM_CASE(VM_S_GT) LLO_VM_CASE(VM_S_DIV) LLO_VM_CASE(VM_S_RDIV)
+			LLO_VM_CASE(VM_S_POW) LLO_VM_CASE(VM_S_RPOW)
+#undef LLO_VM_CASE
 			default: break;
 		}
 	}
 }
 
+#endif // LLO_VM_STATIC
+
+#ifndef __CUDACC_RTC__
 /// Host side: validate and launch (elementwise.cu)
 int vm_launch (llo_cuda_ctx* ctx, int dtype, void* out,
 	const uint64_t outshape[LLO_RANK],
@@ -579,6 +697,7 @@ int vm_launch (llo_cuda_ctx* ctx, int dtype, void* out,
 int vm_prepare (VmParams& p, int dtype, const uint64_t outshape[LLO_RANK],
 	const VmInput* inputs, int ninputs, const void* consts, int nconsts,
 	const llo_cuda_insn* program, int ninsns, int chunk, int span);
+#endif // __CUDACC_RTC__
 
 }
 

@@ -581,6 +581,22 @@ PYBIND11_MODULE(_C, m)
 			out["shared"] = st.shared_;
 			return out;
 		});
+	llo_m.def("set_specialize_min", [](uint64_t elements)
+		{
+			llo::device::check(llo_cuda_set_specialize_min(llo::device::ctx(), elements));
+		}, "elementwise launches of at least this many outputs run a kernel compiled "
+		"for their program (NVRTC, cached); smaller ones run the interpreted kernel");
+	llo_m.def("specialize_stats", []()
+		{
+			uint64_t st[4];
+			llo::device::check(llo_cuda_specialize_stats(llo::device::ctx(), st));
+			py::dict out;
+			out["launches"] = st[0];
+			out["compiles"] = st[1];
+			out["disk_hits"] = st[2];
+			out["failures"] = st[3];
+			return out;
+		});
 	llo_m.def("set_option", &llo::set_option);
 	llo_m.def("get_option", &llo::get_option);
 }

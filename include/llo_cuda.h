@@ -119,6 +119,16 @@ int llo_cuda_event_record (llo_cuda_ctx* ctx, void* event);
 int llo_cuda_event_elapsed_ms (llo_cuda_ctx* ctx, void* start, void* stop, float* ms);
 int llo_cuda_event_destroy (llo_cuda_ctx* ctx, void* event);
 
+/* Run-time specialisation of the fused elementwise engine: launches of at
+ * least `elements` outputs (default 2^20; 0 = every launch, UINT64_MAX = none)
+ * run a build of the kernel compiled for their program with NVRTC (sm_100a,
+ * cached in memory and under LLO_KERNEL_CACHE / beside the library); smaller
+ * ones, and any launch whose build fails, run the interpreted kernel.  Both
+ * apply the same operator code in the same order: results are bit-identical.
+ * stats = {specialised launches, NVRTC compilations, disk-cache hits, failed builds} */
+int llo_cuda_set_specialize_min (llo_cuda_ctx* ctx, uint64_t elements);
+int llo_cuda_specialize_stats (llo_cuda_ctx* ctx, uint64_t stats[4]);
+
 /* ---- K0: leaf dtype conversion, GenericData::copyover
  *      (llo/src/data.cpp:20-72) ---- */
 int llo_cuda_convert (llo_cuda_ctx* ctx, void* out, int out_dtype,

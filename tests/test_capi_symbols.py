@@ -51,3 +51,19 @@ def test_no_gpu_means_loud_failure_not_fallback():
     v = llo.variable(np.ones((2, 3)), "v")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         llo.evaluate(v)
+
+
+def test_nvrtc_stand_in_header_matches_the_real_one():
+    """csrc/cuda/rtc/llo_cuda.h repeats the constants the device code uses (a JIT
+    translation unit may not declare host functions): same values as include/llo_cuda.h"""
+    stub = open(os.path.join(util.ROOT, "cortenn_b200", "csrc", "cuda", "rtc", "llo_cuda.h")).read()
+    real = open(HEADER).read()
+    for name in ("LLO_RANK", "LLO_MAT", "LLO_VM_MAX_INPUTS", "LLO_VM_MAX_INSNS", "LLO_VM_MAX_CONSTS",
+                 "LLO_VM_MAX_DEPTH"):
+        pat = r"#define\s+%s\s+(\d+)" % name
+        assert re.search(pat, stub).group(1) == re.search(pat, real).group(1), name
+
+    def opcodes(text):
+        body = re.search(r"enum\s*\{\s*(LLO_OP_BAD.*?)\}", text, flags=re.S).group(1)
+        return [t.strip().split("=")[0].strip() for t in body.replace("\n", " ").split(",") if t.strip()]
+    assert opcodes(stub) == opcodes(real)
