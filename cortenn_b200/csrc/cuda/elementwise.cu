@@ -566,9 +566,18 @@ static int launch_tile (llo_cuda_ctx* ctx, int dtype, VmParams& p, int nstaged,
 			unsigned pblocks = (unsigned) std::min<uint64_t>(units,
 				(uint64_t) ctx->sm_count * 3);
 			int rc = LLO_OK;
-			if (spec_launch(ctx, SPEC_PAIR4, dtype, p, pblocks, psmem, rc))
+			if (spec_wanted(ctx, p.n))
 			{
-				return rc;
+				// the specialised build has its own ring depth / occupancy
+				int nbuf, ctas;
+				spec_pair_shape(nbuf, ctas);
+				size_t ssmem = (size_t) 2 * nbuf * VM_TS * VM_TS * sizeof(T) + spill;
+				unsigned sblocks = (unsigned) std::min<uint64_t>(units,
+					(uint64_t) ctx->sm_count * ctas);
+				if (spec_launch(ctx, SPEC_PAIR4, dtype, p, sblocks, ssmem, rc))
+				{
+					return rc;
+				}
 			}
 			vm_pair4_kernel<T><<<pblocks, VM_THREADS, psmem, ctx->stream>>>(p);
 			return launched(ctx, "vm_pair4_kernel");

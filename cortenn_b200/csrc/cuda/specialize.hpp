@@ -38,6 +38,13 @@ enum SpecKernel
 bool spec_launch (llo_cuda_ctx* ctx, SpecKernel kernel, int dtype,
 	const VmParams& p, unsigned blocks, size_t smem, int& rc);
 
+/// Shape of the specialised pair kernel: unit buffers in its ring and CTAs per
+/// SM (the launch side sizes shared memory and the grid from it)
+void spec_pair_shape (int& nbuf, int& ctas);
+
+/// True when launches of `n` outputs take the specialised path
+bool spec_wanted (llo_cuda_ctx* ctx, uint64_t n);
+
 /// The NVRTC translation unit for a key, for tests and offline inspection
 std::string spec_source (SpecKernel kernel, int dtype, const VmParams& p);
 

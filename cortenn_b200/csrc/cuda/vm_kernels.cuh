@@ -283,6 +283,8 @@ struct Tile4Loader
 	uint32_t dim1;
 	uint32_t brest;
 	bool full;               // FULL = false: the whole tile lies inside the output
+	const uint4* pre;        // specialised build: row-broadcast operands fetched
+	                         // ahead of the barrier (tile4_prefetch), else null
 
 	__device__ __forceinline__ int valid (int u) const
 	{
@@ -347,7 +349,8 @@ struct Tile4Loader
 				if (0 == kind.s1)
 				{
 					// broadcast along dim 1: the four chunks are the same 16 bytes
-					uint4 tmp = __ldg(reinterpret_cast<const uint4*>(data + off));
+					uint4 tmp = (nullptr != pre) ? pre[k] :
+						__ldg(reinterpret_cast<const uint4*>(data + off));
 					const T* t = reinterpret_cast<const T*>(&tmp);
 #pragma unroll
 					for (int u = 0; u < 4; ++u)
@@ -528,18 +531,50 @@ __device__ __forceinline__ void stage_tiles (const VmParams& p, T* tiles,
 	}
 }
 
+#ifdef LLO_VM_STATIC
+/// Operands that are contiguous along dim 0 and broadcast along dim 1
+/// (extend(b): 16 bytes per thread and tile) do not depend on the staged
+/// tiles, so the specialised build fetches them BEFORE the barrier the tile
+/// waits at instead of stalling on them right behind it (ncu on the chain:
+/// half of all stall samples sat on the multiply that consumes b).
+struct Tile4Pre
+{
+	uint4 v[LLO_VM_S_NINPUTS];
+};
+
+template <int K, typename T>
+__device__ __forceinline__ void tile4_prefetch (Tile4Pre& pre, const VmParams& p,
+	uint32_t c0, uint32_t brest)
+{
+	if constexpr (K < LLO_VM_S_NINPUTS)
+	{
+		if constexpr (VM_IN_STRIDED == LLO_VM_S_MODE[K] && 1 == LLO_VM_S_S0[K] &&
+			0 == LLO_VM_S_S1[K] && 0 != LLO_VM_S_VEC[K])
+		{
+			const VmInput& in = p.in[K];
+			int32_t off = (int32_t) in.offset + rest_offset32(p, in.stride, brest) +
+				(int32_t) c0;
+			pre.v[K] = __ldg(reinterpret_cast<const uint4*>(
+				static_cast<const T*>(in.data) + off));
+		}
+		tile4_prefetch<K + 1,T>(pre, p, c0, brest);
+	}
+}
+#endif
+
 /// Run the program for the output tile at (o0, o1) and store it
 template <typename T, bool FULL>
 __device__ __forceinline__ void run_tile (const VmParams& p,
 	const Tile4Thread& th, const T* tiles, T* spill,
-	uint32_t o0, uint32_t o1, uint32_t brest, const T* alias = nullptr)
+	uint32_t o0, uint32_t o1, uint32_t brest, const T* alias = nullptr,
+	const uint4* pre = nullptr)
 {
 	using G = VmGeom<T>;
 	Tile4Loader<T,FULL> loader = {p, tiles + th.tile_off,
 		alias + th.alias_off, o0 + th.tx4, o1 + th.ty4,
 		(uint32_t) p.dims[0], (uint32_t) p.dims[1], brest,
 		FULL || (o0 + VM_TS <= (uint32_t) p.dims[0] &&
-			o1 + VM_TS <= (uint32_t) p.dims[1])};
+			o1 + VM_TS <= (uint32_t) p.dims[1]), pre};
 	T acc[G::V];
 	// (the compact interpreter for the pair kernel, FULL = true, only:
 	// vm_tile4_kernel lost 2% to it on a plain permute)
@@ -692,15 +727,22 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 /// Staging addresses are affine in the tile indices: everything that depends
 /// on the thread only (source offset inside a tile, swizzled destination) is
 /// computed once per kernel.
+#ifdef LLO_VM_STATIC
+#define LLO_VM_PAIR_RING LLO_VM_PAIR_NBUF
+#define LLO_VM_PAIR_CTAS LLO_VM_PAIR_MINCTAS
+#else
+#define LLO_VM_PAIR_RING 2
+#define LLO_VM_PAIR_CTAS 3
+#endif
 template <typename T>
-__global__ void __launch_bounds__(VM_THREADS, 3)
+__global__ void __launch_bounds__(VM_THREADS, LLO_VM_PAIR_CTAS)
 vm_pair4_kernel (const __grid_constant__ VmParams p)
 {
 	static_assert(4 == sizeof(T), "4-byte element types only");
 	extern __shared__ __align__(16) unsigned char vm_smem[];
 	T* tiles = reinterpret_cast<T*>(vm_smem);
 	constexpr int SLOT = VM_TS * VM_TS;
-	T* spill = tiles + 4 * SLOT;
+	T* spill = tiles + 2 * LLO_VM_PAIR_RING * SLOT;
 	const uint32_t side = p.tiles0;
 	const uint32_t pairs = side * (side - 1) / 2;
 	// work units per slice of the other dims: the off-diagonal pairs, then the
@@ -775,6 +817,98 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 		}
 	};
 
+#ifdef LLO_VM_STATIC
+	// ---- specialised build ------------------------------------------------------
+	// No longer instruction-bound, this build is tuned for bytes in flight
+	// (tools/probes/tile_probe2.cu: a persistent tile loop needs >= 64 KB of
+	// loads outstanding per SM and counter-based hand-out to reach the rate of
+	// a flat copy: 6.1 -> 6.9 TB/s):
+	//   * a ring of NBUF unit buffers (two 16 KB tiles each): the copies of
+	//     units k + 1 .. k + NBUF - 1 are in flight while unit k is computed;
+	//   * units come from the global counter, claimed NBUF iterations ahead by
+	//     thread 0 and published through the ring `uq` (slot m & 3 holds the
+	//     unit of iteration m; it is written between barriers m - NBUF and
+	//     m - NBUF + 1 and last read behind barrier m - 1... m: never both
+	//     between the same two barriers);
+	//   * row-broadcast operands of a unit are fetched ahead of its barrier.
+	constexpr int NBUF = LLO_VM_PAIR_NBUF;
+	static_assert(NBUF >= 2 && NBUF <= 4, "ring depth");
+	__shared__ uint32_t uq[4];
+	UnitClaim units = {p.sched, uq, 0};
+	if (0 == threadIdx.x)
+	{
+		uq[0] = blockIdx.x;
+		for (int m = 1; m < NBUF; ++m)
+		{
+			uq[m] = units.claim();
+		}
+	}
+	__syncthreads();
+	auto stage_unit = [&] (uint32_t unit, int buf)
+	{
+		if (unit < total)
+		{
+			uint32_t si, sj, srest;
+			unit_of(unit, si, sj, srest);
+			stage_pair(buf, si, sj, srest);
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory"); // (possibly empty: keeps the group count in step)
+	};
+	for (int m = 0; m < NBUF - 1; ++m)
+	{
+		stage_unit(uq[m], m);
+	}
+	uint32_t unit = blockIdx.x;
+	for (uint32_t k = 0; unit < total; ++k)
+	{
+		uint32_t i, j, brest;
+		unit_of(unit, i, j, brest);
+		Tile4Pre pre0, pre1;
+		tile4_prefetch<0,T>(pre0, p, ((i < j) ? i : j) * VM_TS + th.tx4, brest);
+		// this unit's copies have landed once at most NBUF - 2 younger groups
+		// are still pending
+		if (NBUF == 2) { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+		if (NBUF == 3) { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+		if (NBUF == 4) { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
+		__syncthreads();
+		// behind barrier k: buffer (k - 1) % NBUF is free again -> unit k + NBUF - 1
+		uint32_t next = uq[(k + 1) & 3];
+		stage_unit(uq[(k + NBUF - 1) & 3], (int) ((k + NBUF - 1) % NBUF));
+		if (0 == threadIdx.x)
+		{
+			units.claimed = units.claim();
+		}
+		int buf = (int) (k % NBUF);
+		T* slot0 = tiles + buf * 2 * SLOT;
+		T* slot1 = slot0 + SLOT;
+		int halves = (i == j) ? 1 : 2;
+		if (2 == halves)
+		{
+			tile4_prefetch<0,T>(pre1, p, ((i < j) ? j : i) * VM_TS + th.tx4, brest);
+		}
+		{
+			const T* other = (i < j) ? slot1 : slot0;
+			uint32_t t0 = (i < j) ? i : j;
+			uint32_t t1 = (i < j) ? j : t0;
+			run_tile<T,true>(p, th, slot0, spill, t0 * VM_TS, t1 * VM_TS, brest, other, pre0.v);
+		}
+		if (2 == halves)
+		{
+			const T* other = (i < j) ? slot0 : slot1;
+			uint32_t t0 = (i < j) ? j : i;
+			uint32_t t1 = (i < j) ? i : t0;
+			run_tile<T,true>(p, th, slot1, spill, t0 * VM_TS, t1 * VM_TS, brest, other, pre1.v);
+		}
+		if (0 == threadIdx.x)
+		{
+			uq[(k + NBUF) & 3] = units.claimed;
+		}
+		unit = next;
+	}
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
+	units.finish();
+#else
+	// ---- interpreted build --------------------------------------------------------
 	// (units go round-robin here: handing them out through the counter, which
 	// helps vm_tile4_kernel, measured 4% slower on this instruction-bound kernel)
 	uint32_t unit = blockIdx.x;    // (the grid never exceeds the unit count)
@@ -821,6 +955,7 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 		j = nj;
 		brest = nrest;
 	}
+#endif
 }
 
 }

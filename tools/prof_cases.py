@@ -41,6 +41,11 @@ def main():
         "extend": ([view(b, [1, 0])], program((capi.VM_LOAD, 0))),
         "mulext": ([view(x, dense), view(b, [1, 0])], program((capi.VM_LOAD, 0), (capi.VM_LOAD, 1), ("PROD", 0))),
         "permute": ([view(x, [side, 1])], program((capi.VM_LOAD, 0))),
+        "pairadd": ([view(x, dense), view(x, [side, 1])], program((capi.VM_LOAD, 0), (capi.VM_LOAD, 1), ("SUM", 0))),
+        "pairexp": ([view(x, dense), view(x, [side, 1])],
+                    program((capi.VM_LOAD, 0), ("EXP", 0), (capi.VM_LOAD, 1), ("SUM", 0))),
+        "pairmulb": ([view(x, dense), view(b, [1, 0]), view(x, [side, 1])],
+                     program((capi.VM_LOAD, 0), (capi.VM_LOAD, 1), ("PROD", 0), (capi.VM_LOAD, 2), ("SUM", 0))),
         "chain": ([view(x, dense), view(b, [1, 0]), view(x, [side, 1])],
                   program((capi.VM_LOAD, 0), ("EXP", 0), (capi.VM_LOAD, 1), ("PROD", 0), (capi.VM_LOAD, 2), ("SUM", 0))),
     }
