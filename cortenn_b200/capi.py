@@ -104,6 +104,8 @@ EXPORTS = {
     "llo_cuda_comm_rank": (C.c_int, [C.c_void_p]),
     "llo_cuda_comm_size": (C.c_int, [C.c_void_p]),
     "llo_cuda_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int]),
+    "llo_cuda_allreduce_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
+    "llo_cuda_comm_join": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

@@ -193,6 +193,15 @@ int llo_cuda_comm_init (llo_cuda_ctx* ctx, int rank, int nranks,
 
 int llo_cuda_comm_destroy (llo_cuda_ctx* ctx)
 {
+	if (nullptr != ctx->comm_stream)
+	{
+		cudaStreamSynchronize(ctx->comm_stream);
+		cudaStreamDestroy(ctx->comm_stream);
+		cudaEventDestroy(ctx->comm_ready);
+		cudaEventDestroy(ctx->comm_done);
+		ctx->comm_stream = nullptr;
+		ctx->comm_pending = false;
+	}
 	if (nullptr != ctx->comm)
 	{
 		cudaStreamSynchronize(ctx->stream);
@@ -212,6 +221,62 @@ int llo_cuda_comm_rank (llo_cuda_ctx* ctx)
 int llo_cuda_comm_size (llo_cuda_ctx* ctx)
 {
 	return ctx->comm_size;
+}
+
+int llo_cuda_allreduce_async (llo_cuda_ctx* ctx, void* buf, uint64_t n,
+	int dtype, int opcode)
+{
+	if (false == is_nnary_op(opcode))
+	{
+		return fail(LLO_ERR_FATAL, "cannot allreduce with %s", op_name(opcode));
+	}
+	if (ctx->comm_size <= 1 || 0 == n)
+	{
+		return LLO_OK;
+	}
+	int ntype = nccl_dtype(dtype);
+	if (ntype < 0)
+	{
+		return fail(LLO_ERR_FATAL, "cannot allreduce %s", dtype_name(dtype));
+	}
+	if (nullptr == ctx->comm)
+	{
+		return fail(LLO_ERR_FATAL, "the context has no communicator "
+			"(llo_cuda_comm_init)");
+	}
+	if (nullptr == ctx->comm_stream)
+	{
+		LLO_CUDA_TRY(cudaSetDevice(ctx->device));
+		LLO_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+		LLO_CUDA_TRY(cudaEventCreateWithFlags(&ctx->comm_ready, cudaEventDisableTiming));
+		LLO_CUDA_TRY(cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming));
+	}
+	// the collective starts when everything queued on the stream so far (the
+	// kernels that produced `buf`) has finished, and runs beside what is
+	// queued afterwards
+	LLO_CUDA_TRY(cudaEventRecord(ctx->comm_ready, ctx->stream));
+	LLO_CUDA_TRY(cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_ready, 0));
+	int nop = LLO_OP_SUM == opcode ? NCCL_SUM : (LLO_OP_PROD == opcode ?
+		NCCL_PROD : (LLO_OP_MIN == opcode ? NCCL_MIN : NCCL_MAX));
+	NcclResult rc = nccl().all_reduce(buf, buf, n, ntype, nop,
+		(NcclComm) ctx->comm, ctx->comm_stream);
+	if (0 != rc)
+	{
+		return fail_nccl(rc, "ncclAllReduce");
+	}
+	ctx->comm_pending = true;
+	return LLO_OK;
+}
+
+int llo_cuda_comm_join (llo_cuda_ctx* ctx)
+{
+	if (ctx->comm_pending)
+	{
+		LLO_CUDA_TRY(cudaEventRecord(ctx->comm_done, ctx->comm_stream));
+		LLO_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->comm_done, 0));
+		ctx->comm_pending = false;
+	}
+	return LLO_OK;
 }
 
 int llo_cuda_allreduce (llo_cuda_ctx* ctx, void* buf, uint64_t n, int dtype,

@@ -57,6 +57,12 @@ struct llo_cuda_ctx
 	void* comm = nullptr;
 	int comm_rank = 0;
 	int comm_size = 1;
+	// second lane for collectives that overlap later compute
+	// (llo_cuda_allreduce_async / llo_cuda_comm_join)
+	cudaStream_t comm_stream = nullptr;
+	cudaEvent_t comm_ready = nullptr;   // recorded on `stream`: the bucket is complete
+	cudaEvent_t comm_done = nullptr;    // recorded on comm_stream: collectives so far are done
+	bool comm_pending = false;
 	// run-time specialisation of the elementwise engine (specialize.cu):
 	// launches of at least spec_min output elements use the NVRTC build
 	uint64_t spec_min = 1ull << 20;

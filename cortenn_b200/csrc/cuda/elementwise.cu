@@ -568,6 +568,10 @@ static int launch_tile (llo_cuda_ctx* ctx, int dtype, VmParams& p, int nstaged,
 			int rc = LLO_OK;
 			if (spec_wanted(ctx, p.n))
 			{
+				if (spec_launch_pair_tma(ctx, dtype, p, units, spill, rc))
+				{
+					return rc;
+				}
 				// the specialised build has its own ring depth / occupancy
 				int nbuf, ctas;
 				spec_pair_shape(nbuf, ctas);

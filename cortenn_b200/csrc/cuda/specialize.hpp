@@ -29,6 +29,7 @@ enum SpecKernel
 	SPEC_TILE4_ALIGNED,
 	SPEC_TILE4_UNALIGNED,
 	SPEC_PAIR4,
+	SPEC_PAIR4_TMA,      // TMA-staged, warp-specialised form of SPEC_PAIR4
 };
 
 /// Launch the specialised build of `kernel` for program `p` if the launch is
@@ -37,6 +38,13 @@ enum SpecKernel
 /// should launch the interpreted kernel.
 bool spec_launch (llo_cuda_ctx* ctx, SpecKernel kernel, int dtype,
 	const VmParams& p, unsigned blocks, size_t smem, int& rc);
+
+/// SPEC_PAIR4_TMA: builds the tensor map of the pair program's staged input
+/// (the 4-D / 5-D view described at tile4_thread_tma) and launches the
+/// TMA-staged kernel.  False when the shape does not fit the view (the caller
+/// then tries SPEC_PAIR4) or the build is unavailable.
+bool spec_launch_pair_tma (llo_cuda_ctx* ctx, int dtype, const VmParams& p,
+	uint64_t units, size_t spill, int& rc);
 
 /// Shape of the specialised pair kernel: unit buffers in its ring and CTAs per
 /// SM (the launch side sizes shared memory and the grid from it)

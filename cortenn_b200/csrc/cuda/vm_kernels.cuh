@@ -253,9 +253,31 @@ struct Tile4Thread
 {
 	uint32_t tx4;        // 4 tx: first dim-0 coordinate inside the tile
 	uint32_t ty4;        // 4 ty: first dim-1 coordinate inside the tile
-	uint32_t tile_off;   // transposed read, e = 0 (row 4 tx, chunk ty); +64 per e
+	uint32_t tile_off;   // transposed read, e = 0 (row 4 tx, chunk ty); +step per e
 	uint32_t alias_off;  // straight read of the mirror tile, u = 0 (row 4 ty, chunk tx)
+	uint32_t step;       // elements between the rows 4 t + e and 4 t + e + 1 of a tile
 };
+
+/// Positions for tiles written by TMA (vm_pair4_tma_kernel): the tile is
+/// fetched through a 4-D view of the tensor -- (p % 32, r / 4, r % 4, p / 32)
+/// -- with the 128-byte hardware swizzle, so that row r of the tile lands in
+/// shared-memory row s = (r % 4) * 16 + r / 4 of the half p / 32 and its
+/// 16-byte chunks are XORed with s % 8 = (r / 4) % 8: the key the conflict-free
+/// 4 x 4 register transposition needs (rows 4 t + e of eight neighbouring
+/// lanes get eight different keys), from a swizzle the hardware only offers
+/// as a function of the shared-memory row.
+__device__ __forceinline__ Tile4Thread tile4_thread_tma ()
+{
+	uint32_t tx = threadIdx.x & 15;
+	uint32_t ty = threadIdx.x >> 4;
+	Tile4Thread th;
+	th.tx4 = 4 * tx;
+	th.ty4 = 4 * ty;
+	th.tile_off = (ty >> 3) * 2048 + tx * 32 + (((ty & 7) ^ (tx & 7)) << 2);
+	th.alias_off = (tx >> 3) * 2048 + ty * 32 + (((tx & 7) ^ (ty & 7)) << 2);
+	th.step = 16 * 32;
+	return th;
+}
 
 __device__ __forceinline__ Tile4Thread tile4_thread ()
 {
@@ -266,6 +288,7 @@ __device__ __forceinline__ Tile4Thread tile4_thread ()
 	th.ty4 = 4 * ty;
 	th.tile_off = 4 * tx * VM_TS + ((ty ^ (tx & 7)) << 2);
 	th.alias_off = 4 * ty * VM_TS + ((tx ^ (ty & 7)) << 2);
+	th.step = VM_TS;
 	return th;
 }
 
@@ -285,6 +308,7 @@ struct Tile4Loader
 	bool full;               // FULL = false: the whole tile lies inside the output
 	const uint4* pre;        // specialised build: row-broadcast operands fetched
 	                         // ahead of the barrier (tile4_prefetch), else null
+	uint32_t step;           // Tile4Thread::step
 
 	__device__ __forceinline__ int valid (int u) const
 	{
@@ -310,7 +334,7 @@ struct Tile4Loader
 #pragma unroll
 			for (int e = 0; e < 4; ++e)
 			{
-				uint4 tmp = *reinterpret_cast<const uint4*>(src + e * VM_TS);
+				uint4 tmp = *reinterpret_cast<const uint4*>(src + e * step);
 				const T* t = reinterpret_cast<const T*>(&tmp);
 #pragma unroll
 				for (int u = 0; u < 4; ++u)
@@ -327,7 +351,7 @@ struct Tile4Loader
 #pragma unroll
 			for (int u = 0; u < 4; ++u)
 			{
-				uint4 tmp = *reinterpret_cast<const uint4*>(alias_rd + u * VM_TS);
+				uint4 tmp = *reinterpret_cast<const uint4*>(alias_rd + u * step);
 				const T* t = reinterpret_cast<const T*>(&tmp);
 #pragma unroll
 				for (int e = 0; e < 4; ++e)
@@ -574,7 +598,7 @@ __device__ __forceinline__ void run_tile (const VmParams& p,
 		alias + th.alias_off, o0 + th.tx4, o1 + th.ty4,
 		(uint32_t) p.dims[0], (uint32_t) p.dims[1], brest,
 		FULL || (o0 + VM_TS <= (uint32_t) p.dims[0] &&
-			o1 + VM_TS <= (uint32_t) p.dims[1]), pre};
+			o1 + VM_TS <= (uint32_t) p.dims[1]), pre, th.step};
 	T acc[G::V];
 	// (the compact interpreter for the pair kernel, FULL = true, only:
 	// vm_tile4_kernel lost 2% to it on a plain permute)
@@ -718,6 +742,37 @@ vm_tile4_kernel (const __grid_constant__ VmParams p)
 	}
 }
 
+/// q-th strictly-lower index pair of the triangular numbering: q = b (b - 1) / 2 + a, a < b
+__device__ __forceinline__ void tri_index (uint32_t q, uint32_t& a, uint32_t& b)
+{
+	uint32_t bb = (uint32_t) ((1.0f + sqrtf(1.0f + 8.0f * (float) q)) * 0.5f);
+	while (bb * (bb - 1) / 2 > q) { --bb; }
+	while ((bb + 1) * bb / 2 <= q) { ++bb; }
+	b = bb;
+	a = q - bb * (bb - 1) / 2;
+}
+
+/// Work unit q of one slice of the pair kernels -> (i, j): i < j names the tile
+/// pair {(i,j), (j,i)}; i > j the diagonal tiles (j,j) and (i,i) = (j+1,j+1);
+/// i == j one diagonal tile.  Consecutive units share j, so the mirror tiles
+/// (j, i), (j, i + 1) of units that run at the same time are neighbours along
+/// the contiguous direction.  (Walking the triangle in 8 x 8 blocks of tiles,
+/// which gives both tiles of a pair such neighbours, measured no better:
+/// 0.356 vs 0.351 ms on the chain, round 2.)
+__device__ __forceinline__ void pair_unit (uint32_t q, uint32_t side,
+	uint32_t pairs, uint32_t& i, uint32_t& j)
+{
+	if (q < pairs)
+	{
+		tri_index(q, i, j);
+	}
+	else
+	{
+		j = 2 * (q - pairs);
+		i = j + 1 < side ? j + 1 : j;
+	}
+}
+
 /// Pair mode (x and permute(x) in one program, square grid of full tiles): a
 /// CTA takes the tile pair {(i,j), (j,i)}, stages the two input tiles ONCE
 /// (cp.async, two slots, double buffered over pairs) and computes both output
@@ -769,20 +824,7 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 	auto unit_of = [&] (uint32_t unit, uint32_t& i, uint32_t& j, uint32_t& brest)
 	{
 		brest = unit / per;
-		uint32_t q = unit - brest * per;
-		if (q < pairs)
-		{
-			uint32_t jj = (uint32_t) ((1.0f + sqrtf(1.0f + 8.0f * (float) q)) * 0.5f);
-			while (jj * (jj - 1) / 2 > q) { --jj; }
-			while ((jj + 1) * jj / 2 <= q) { ++jj; }
-			j = jj;
-			i = q - jj * (jj - 1) / 2;
-		}
-		else
-		{
-			j = 2 * (q - pairs);
-			i = j + 1 < side ? j + 1 : j;
-		}
+		pair_unit(unit - brest * per, side, pairs, i, j);
 	};
 	// input tile of output tile (ti, tj) -> the slot at shared address `slot`
 	auto stage_one = [&] (uint32_t slot, uint32_t ti, uint32_t tj, int32_t rest)
@@ -957,6 +999,219 @@ vm_pair4_kernel (const __grid_constant__ VmParams p)
 	}
 #endif
 }
+
+#ifdef LLO_VM_STATIC
+
+// ---- pair kernel, TMA-staged and warp-specialised (specialised build only) ------
+//
+// Same work units and the same math as vm_pair4_kernel; what changes is how the
+// tiles arrive and who waits for what:
+//   * one elected lane of a ninth warp is the producer: it claims units from the
+//     global counter, and per unit issues TWO bulk tensor copies
+//     (cp.async.bulk.tensor.4d/5d -> SASS UTMALDG) instead of 256 threads x 8
+//     LDGSTS with their address arithmetic;
+//   * tiles land in the layout of tile4_thread_tma (4-D view + 128-byte swizzle);
+//   * full / empty mbarriers per unit buffer replace the CTA-wide barrier: a
+//     consumer warp that is done with a unit moves on to the next one while its
+//     neighbours are still storing, and the producer refills a buffer as soon as
+//     the eighth warp has released it.
+
+struct alignas(64) VmTensorMap
+{
+	unsigned long long opaque[16];   // CUtensorMap
+};
+
+__device__ __forceinline__ uint32_t vm_smem_u32 (const void* ptr)
+{
+	return (uint32_t) __cvta_generic_to_shared(ptr);
+}
+
+__device__ __forceinline__ void vm_mbar_init (uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;"
+		:: "r"(vm_smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void vm_mbar_expect_tx (uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+		:: "r"(vm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void vm_mbar_arrive (uint64_t* bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];"
+		:: "r"(vm_smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void vm_mbar_wait (uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred P1;\n"
+		"VM_WAIT:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+		"@P1 bra VM_DONE;\n"
+		"bra VM_WAIT;\n"
+		"VM_DONE:\n"
+		"}" :: "r"(vm_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+/// one 64 x 64 tile: box (32, 16, 4, 2[, 1]) of the (p % 32, r / 4, r % 4, p / 32[, rest]) view
+template <int RANK>
+__device__ __forceinline__ void vm_tma_tile (void* dst, const VmTensorMap* map,
+	uint64_t* bar, uint32_t row_tile, uint32_t col_tile, uint32_t rest)
+{
+	if constexpr (4 == RANK)
+	{
+		asm volatile(
+			"cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+			" [%0], [%1, {%3, %4, %5, %6}], [%2];"
+			:: "r"(vm_smem_u32(dst)), "l"(map), "r"(vm_smem_u32(bar)),
+			"r"(0), "r"((int) (row_tile * 16)), "r"(0), "r"((int) (col_tile * 2))
+			: "memory");
+	}
+	else
+	{
+		asm volatile(
+			"cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+			" [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+			:: "r"(vm_smem_u32(dst)), "l"(map), "r"(vm_smem_u32(bar)),
+			"r"(0), "r"((int) (row_tile * 16)), "r"(0), "r"((int) (col_tile * 2)),
+			"r"((int) rest)
+			: "memory");
+	}
+}
+
+template <typename T>
+__global__ void __launch_bounds__(VM_THREADS + 32, LLO_VM_PAIR_MINCTAS)
+vm_pair4_tma_kernel (const __grid_constant__ VmParams p,
+	const __grid_constant__ VmTensorMap tmap)
+{
+	static_assert(4 == sizeof(T), "4-byte element types only");
+	constexpr int NBUF = LLO_VM_PAIR_NBUF;
+	constexpr int SLOT = VM_TS * VM_TS;
+	constexpr int MAP_RANK = (LLO_VM_STATIC_NDIMS == 3) ? 5 : 4;
+	extern __shared__ __align__(16) unsigned char vm_smem[];
+	// swizzled TMA destinations start on 1024-byte boundaries
+	unsigned char* base = vm_smem + ((1024u - (vm_smem_u32(vm_smem) & 1023u)) & 1023u);
+	T* tiles = reinterpret_cast<T*>(base);
+	T* spill = tiles + 2 * NBUF * SLOT;
+	__shared__ uint64_t full[NBUF];
+	__shared__ uint64_t empty[NBUF];
+	__shared__ uint32_t uq[NBUF];
+
+	const uint32_t side = p.tiles0;
+	const uint32_t pairs = side * (side - 1) / 2;
+	const uint32_t per = pairs + (side + 1) / 2;
+	const uint32_t total = p.total_tiles;
+	auto unit_of = [&] (uint32_t unit, uint32_t& i, uint32_t& j, uint32_t& brest)
+	{
+		brest = unit / per;
+		pair_unit(unit - brest * per, side, pairs, i, j);
+	};
+
+	if (0 == threadIdx.x)
+	{
+		for (int b = 0; b < NBUF; ++b)
+		{
+			vm_mbar_init(&full[b], 1);
+			vm_mbar_init(&empty[b], VM_THREADS / 32);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap) : "memory");
+	}
+	__syncthreads();
+
+	if (threadIdx.x >= VM_THREADS)
+	{
+		// ---- producer warp: one elected lane ----
+		if (VM_THREADS == threadIdx.x)
+		{
+			UnitClaim units = {p.sched, uq, 0};
+			uint32_t unit = blockIdx.x;
+			uint32_t ahead = units.claim();   // claimed one unit early: the atomic's
+			                                  // round trip hides under a buffer wait
+			for (uint32_t k = 0; ; ++k)
+			{
+				uint32_t b = k % NBUF;
+				if (k >= NBUF)
+				{
+					vm_mbar_wait(&empty[b], ((k / NBUF) & 1) ^ 1);
+				}
+				uq[b] = unit;
+				if (unit >= total)
+				{
+					vm_mbar_arrive(&full[b]);   // the consumers' stop sign
+					break;
+				}
+				uint32_t i, j, brest;
+				unit_of(unit, i, j, brest);
+				T* slot0 = tiles + b * 2 * SLOT;
+				// pair: slot 0 <- input tile of output (i,j), slot 1 <- that of (j,i);
+				// diagonal: slot 0 <- tile (j,j), slot 1 <- tile (i,i)
+				uint32_t a0 = (i < j) ? i : j, a1 = j;
+				uint32_t b0 = (i < j) ? j : i, b1 = i;
+				bool two = i != j;
+				vm_mbar_expect_tx(&full[b], (two ? 2u : 1u) * SLOT * 4u);
+				vm_tma_tile<MAP_RANK>(slot0, &tmap, &full[b], a0, a1, brest);
+				if (two)
+				{
+					vm_tma_tile<MAP_RANK>(slot0 + SLOT, &tmap, &full[b], b0, b1, brest);
+				}
+				unit = ahead;
+				ahead = units.claim();
+			}
+			// the last CTA out re-arms the counter for the next launch
+			__threadfence();
+			if (gridDim.x - 1 == atomicAdd(p.sched + 1, 1u))
+			{
+				p.sched[0] = 0;
+				p.sched[1] = 0;
+				__threadfence();
+			}
+		}
+		return;
+	}
+
+	// ---- consumer warps ----
+	const Tile4Thread th = tile4_thread_tma();
+	const uint32_t lane = threadIdx.x & 31;
+	for (uint32_t k = 0; ; ++k)
+	{
+		uint32_t b = k % NBUF;
+		vm_mbar_wait(&full[b], (k / NBUF) & 1);
+		uint32_t unit = uq[b];
+		if (unit >= total)
+		{
+			break;
+		}
+		uint32_t i, j, brest;
+		unit_of(unit, i, j, brest);
+		T* slot0 = tiles + b * 2 * SLOT;
+		T* slot1 = slot0 + SLOT;
+		{
+			const T* other = (i < j) ? slot1 : slot0;
+			uint32_t t0 = (i < j) ? i : j;
+			uint32_t t1 = (i < j) ? j : t0;
+			run_tile<T,true>(p, th, slot0, spill, t0 * VM_TS, t1 * VM_TS, brest, other);
+		}
+		if (i != j)
+		{
+			const T* other = (i < j) ? slot0 : slot1;
+			uint32_t t0 = (i < j) ? j : i;
+			uint32_t t1 = (i < j) ? i : t0;
+			run_tile<T,true>(p, th, slot1, spill, t0 * VM_TS, t1 * VM_TS, brest, other);
+		}
+		__syncwarp();
+		if (0 == lane)
+		{
+			vm_mbar_arrive(&empty[b]);
+		}
+	}
+}
+
+#endif // LLO_VM_STATIC
 
 }
 

@@ -244,6 +244,15 @@ int llo_cuda_comm_rank (llo_cuda_ctx* ctx);
 int llo_cuda_comm_size (llo_cuda_ctx* ctx);
 int llo_cuda_allreduce (llo_cuda_ctx* ctx, void* buf, uint64_t n, int dtype,
 	int opcode, int mode);
+/* The same fold (LLO_ALLREDUCE_FAST) on a second lane: it starts once the work
+ * queued on the context's stream so far has finished and runs beside the work
+ * queued afterwards, so the gradients of the last layers travel over NVLink
+ * while the earlier layers' backward GEMMs still run.  llo_cuda_comm_join makes
+ * the stream's later work (and llo_cuda_sync / d2h) wait for every collective
+ * started so far.  Calls must be made in the same order on every rank. */
+int llo_cuda_allreduce_async (llo_cuda_ctx* ctx, void* buf, uint64_t n,
+	int dtype, int opcode);
+int llo_cuda_comm_join (llo_cuda_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@
 
 __device__ uint32_t counter;
 
-template <int INFLIGHT, bool DYNAMIC, int CTAS>
+template <int INFLIGHT, bool DYNAMIC, int CTAS, int ORDER = 0>
 __global__ void __launch_bounds__(256, CTAS) tile_copy (const uint4* __restrict__ src,
 	uint4* __restrict__ dst, uint32_t side_chunks, uint32_t rows, uint32_t persistent)
 {
@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(256, CTAS) tile_copy (const uint4* __restrict_
 		{
 			uint32_t tile = t * INFLIGHT + f;
 			uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
+			if (1 == ORDER) { tx = tile / tiles_x; ty = tile % tiles_x; }   // column-major: no concurrent row neighbours
+			if (2 == ORDER) { uint32_t blk = tile / 16, in = tile % 16; uint32_t bx = blk % (tiles_x / 4), by = blk / (tiles_x / 4); tx = bx * 4 + in % 4; ty = by * 4 + in / 4; }
 #pragma unroll
 			for (int q = 0; q < 4; ++q)
 			{
@@ -37,6 +39,8 @@ __global__ void __launch_bounds__(256, CTAS) tile_copy (const uint4* __restrict_
 		{
 			uint32_t tile = t * INFLIGHT + f;
 			uint32_t ty = tile / tiles_x, tx = tile % tiles_x;
+			if (1 == ORDER) { tx = tile / tiles_x; ty = tile % tiles_x; }
+			if (2 == ORDER) { uint32_t blk = tile / 16, in = tile % 16; uint32_t bx = blk % (tiles_x / 4), by = blk / (tiles_x / 4); tx = bx * 4 + in % 4; ty = by * 4 + in / 4; }
 #pragma unroll
 			for (int q = 0; q < 4; ++q)
 			{
@@ -62,7 +66,7 @@ __global__ void __launch_bounds__(256, CTAS) tile_copy (const uint4* __restrict_
 	}
 }
 
-template <int INFLIGHT, bool DYNAMIC, int CTAS>
+template <int INFLIGHT, bool DYNAMIC, int CTAS, int ORDER = 0>
 void run (const char* what, const uint4* src, uint4* dst, uint32_t side, bool persistent)
 {
 	uint32_t side_chunks = side / 4;
@@ -76,7 +80,7 @@ void run (const char* what, const uint4* src, uint4* dst, uint32_t side, bool pe
 		uint32_t zero = 0;
 		cudaMemcpyToSymbol(counter, &zero, 4);
 		cudaEventRecord(e0);
-		tile_copy<INFLIGHT,DYNAMIC,CTAS><<<persistent ? 148 * CTAS : units, 256>>>(src, dst, side_chunks, side, persistent ? 1 : 0);
+		tile_copy<INFLIGHT,DYNAMIC,CTAS,ORDER><<<persistent ? 148 * CTAS : units, 256>>>(src, dst, side_chunks, side, persistent ? 1 : 0);
 		cudaEventRecord(e1);
 		cudaEventSynchronize(e1);
 		float ms;
@@ -103,6 +107,10 @@ int main ()
 	run<2,true,3>("persistent 3 CTA/SM, 2 tiles, counter", src, dst, side, true);
 	run<2,true,4>("persistent 4 CTA/SM, 2 tiles, counter", src, dst, side, true);
 	run<4,true,2>("persistent 2 CTA/SM, 4 tiles, counter", src, dst, side, true);
+	run<1,true,3,1>("persistent 3 CTA/SM, 1 tile, counter, col-major", src, dst, side, true);
+	run<2,true,3,1>("persistent 3 CTA/SM, 2 tiles, counter, col-major", src, dst, side, true);
+	run<1,true,3,2>("persistent 3 CTA/SM, 1 tile, counter, 4x4 blocks", src, dst, side, true);
+	run<2,true,3,2>("persistent 3 CTA/SM, 2 tiles, counter, 4x4 blocks", src, dst, side, true);
 	run<1,false,8>("grid of tiles (one per CTA)", src, dst, side, false);
 	run<2,false,4>("grid of tile pairs (one pair per CTA)", src, dst, side, false);
 	return 0;
