@@ -198,10 +198,19 @@ __device__ __forceinline__ VmKind vm_kind (const VmParams& p, int k)
 }
 
 #ifdef LLO_VM_STATIC
-// the specialised build knows the collapsed rank when it is 2 or 3 (0 = any)
+// the specialised build knows the collapsed rank when it is 1..3 (0 = any) and
+// the launch-wide addressing flags
 #define LLO_VM_NDIMS(p) (LLO_VM_STATIC_NDIMS > 0 ? LLO_VM_STATIC_NDIMS : (p).ndims)
+#define LLO_VM_IDX32(p) (0 != LLO_VM_S_IDX32)
+#define LLO_VM_ROW_UNIFORM(p) (0 != LLO_VM_S_ROW_UNIFORM)
+#define LLO_VM_ROWS_ALIGNED(p) (0 != LLO_VM_S_ROWS_ALIGNED)
+#define LLO_VM_OUT_VEC(p) (0 != LLO_VM_S_OUT_VEC)
 #else
 #define LLO_VM_NDIMS(p) ((p).ndims)
+#define LLO_VM_IDX32(p) (0 != (p).idx32)
+#define LLO_VM_ROW_UNIFORM(p) (0 != (p).row_uniform)
+#define LLO_VM_ROWS_ALIGNED(p) (0 != (p).rows_aligned)
+#define LLO_VM_OUT_VEC(p) (0 != (p).out_vec_ok)
 #endif
 
 /// E elements from `src`: one 128-bit load when aligned and complete, scalar
@@ -268,7 +277,7 @@ __device__ __forceinline__ void store_chunk (T* dst, const T* src,
 __device__ __forceinline__ int64_t strided_offset (const VmParams& p,
 	const VmInput& in, uint64_t i)
 {
-	if (p.idx32)
+	if (LLO_VM_IDX32(p))
 	{
 		uint32_t rem = (uint32_t) i;
 		int32_t off = (int32_t) in.offset;
@@ -345,14 +354,14 @@ __device__ __forceinline__ T load_element (const VmParams& p, int k, uint64_t i)
 
 /// Input access of the flat launch.  Chunk u of thread t covers the outputs
 /// [base + (u * 256 + t) * E, +E)
-template <typename T>
+template <typename T, bool FULL = false>
 struct FlatLoader
 {
 	using G = VmGeom<T>;
 
 	const VmParams& p;
 	uint64_t base;   // first output of this CTA
-	bool full;       // the CTA's 256 * V outputs all exist
+	bool full;       // the CTA's 256 * V outputs all exist (FULL: known statically)
 
 	__device__ __forceinline__ uint64_t first (int u) const
 	{
@@ -361,7 +370,7 @@ struct FlatLoader
 
 	__device__ __forceinline__ int valid (int u) const
 	{
-		if (full)
+		if (FULL || full)
 		{
 			return G::E;
 		}
@@ -404,7 +413,7 @@ struct FlatLoader
 				}
 			}
 		}
-		else if (p.row_uniform)
+		else if (LLO_VM_ROW_UNIFORM(p))
 		{
 			// the CTA sits inside one row: only the dim-0 coordinate moves
 			int64_t off = strided_offset(p, in, first(0));
@@ -416,7 +425,7 @@ struct FlatLoader
 					G::E);
 			}
 		}
-		else if (p.rows_aligned)
+		else if (LLO_VM_ROWS_ALIGNED(p))
 		{
 			// a chunk shares every coordinate but the fastest
 #pragma unroll

@@ -22,6 +22,23 @@ namespace llo_cuda
 
 // ---- flat launch: 256 threads x V consecutive outputs per CTA -------------------
 
+template <typename T, bool FULL>
+__device__ __forceinline__ void vm_flat_body (const VmParams& p, uint64_t base,
+	bool full, T* spill)
+{
+	using G = VmGeom<T>;
+	FlatLoader<T,FULL> loader = {p, base, full};
+	T acc[G::V];
+	vm_exec<T>(acc, p, loader, spill);
+	T* out = static_cast<T*>(p.out) + loader.first(0);
+#pragma unroll
+	for (int u = 0; u < G::U; ++u)
+	{
+		store_chunk<T,G::E>(out + u * VM_THREADS * G::E, acc + u * G::E,
+			LLO_VM_OUT_VEC(p), loader.valid(u));
+	}
+}
+
 template <typename T>
 __global__ void __launch_bounds__(VM_THREADS, 4)
 vm_flat_kernel (const __grid_constant__ VmParams p)
@@ -29,16 +46,17 @@ vm_flat_kernel (const __grid_constant__ VmParams p)
 	using G = VmGeom<T>;
 	extern __shared__ __align__(16) unsigned char vm_smem[];
 	uint64_t base = (uint64_t) blockIdx.x * (VM_THREADS * G::V);
-	FlatLoader<T> loader = {p, base, base + VM_THREADS * G::V <= p.n};
-	T acc[G::V];
-	vm_exec<T>(acc, p, loader, reinterpret_cast<T*>(vm_smem));
-	T* out = static_cast<T*>(p.out) + loader.first(0);
-#pragma unroll
-	for (int u = 0; u < G::U; ++u)
+	bool full = base + VM_THREADS * G::V <= p.n;
+#ifdef LLO_VM_STATIC
+	// the specialised program is short: a copy without any tail handling for
+	// the CTAs that lie wholly inside the output, the general one for the last
+	if (full)
 	{
-		store_chunk<T,G::E>(out + u * VM_THREADS * G::E, acc + u * G::E,
-			p.out_vec_ok, loader.valid(u));
+		vm_flat_body<T,true>(p, base, true, reinterpret_cast<T*>(vm_smem));
+		return;
 	}
+#endif
+	vm_flat_body<T,false>(p, base, full, reinterpret_cast<T*>(vm_smem));
 }
 
 // ---- tile launch: transposed inputs staged through shared memory ---------------
@@ -190,7 +208,7 @@ vm_tile_kernel (const __grid_constant__ VmParams p)
 		if (ok > 0)
 		{
 			store_chunk<T,G::E>(out + (int64_t) (16 * u) * p.out_stride[1],
-				acc + u * G::E, p.out_vec_ok, ok);
+				acc + u * G::E, LLO_VM_OUT_VEC(p), ok);
 		}
 	}
 }
@@ -606,7 +624,7 @@ __device__ __forceinline__ void run_tile (const VmParams& p,
 	int32_t os1 = (int32_t) p.out_stride[1];
 	T* out = static_cast<T*>(p.out) + rest_offset32(p, p.out_stride, brest) +
 		(int32_t) loader.c0 + (int32_t) loader.c1 * os1;
-	if (loader.full && p.out_vec_ok)
+	if (loader.full && LLO_VM_OUT_VEC(p))
 	{
 #pragma unroll
 		for (int u = 0; u < 4; ++u)
@@ -628,7 +646,7 @@ __device__ __forceinline__ void run_tile (const VmParams& p,
 		int ok = loader.valid(u);
 		if (ok > 0)
 		{
-			store_chunk<T,4>(out + u * os1, acc + u * 4, p.out_vec_ok, ok);
+			store_chunk<T,4>(out + u * os1, acc + u * 4, LLO_VM_OUT_VEC(p), ok);
 		}
 	}
 }

@@ -26,7 +26,7 @@ def nvrtc():
 def tables(sel, arg, mode, s0, s1, vec, ndims):
     def row(name, vals):
         return "static constexpr int %s[] = {%s};\n" % (name, ", ".join(map(str, vals)))
-    return ("#define LLO_VM_STATIC 1\n#define LLO_VM_PAIR_NBUF 2\n#define LLO_VM_PAIR_MINCTAS 3\n#define LLO_VM_STATIC_NDIMS %d\n#define LLO_VM_S_NINSNS %d\n#define LLO_VM_S_NINPUTS %d\n" % (ndims, len(sel), len(mode)) +
+    return ("#define LLO_VM_STATIC 1\n#define LLO_VM_S_IDX32 1\n#define LLO_VM_S_ROW_UNIFORM 0\n#define LLO_VM_S_ROWS_ALIGNED 1\n#define LLO_VM_S_OUT_VEC 1\n#define LLO_VM_PAIR_NBUF 2\n#define LLO_VM_PAIR_MINCTAS 3\n#define LLO_VM_STATIC_NDIMS %d\n#define LLO_VM_S_NINSNS %d\n#define LLO_VM_S_NINPUTS %d\n" % (ndims, len(sel), len(mode)) +
             row("LLO_VM_S_SEL", sel) + row("LLO_VM_S_ARG", arg) + row("LLO_VM_S_MODE", mode) +
             row("LLO_VM_S_S0", s0) + row("LLO_VM_S_S1", s1) + row("LLO_VM_S_VEC", vec))
 
