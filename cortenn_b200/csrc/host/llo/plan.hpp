@@ -26,6 +26,8 @@
 /// product rule introduces (llo/src/helper.cpp:18-33).
 ///
 
+#include <functional>
+
 #include "llo/data.hpp"
 
 #ifndef LLO_PLAN_HPP
@@ -53,8 +55,16 @@ struct PlanStats
 GenericData planned_eval (ade::TensptrT root, age::_GENERATED_DTYPE dtype);
 
 /// Evaluate several roots in one plan (shared sub-graphs computed once)
+/// `dests` (optional, one per root, null entries allowed): device blocks the
+/// results are to end up in -- a root that computes writes there directly (no
+/// copy; the packed gradient buffer of the sharded evaluator).  `on_done(i)`
+/// (optional) is called when everything root i needs has been enqueued, in
+/// root order: the hook that starts root i's collective while the later
+/// roots are still being computed.
 std::vector<GenericData> planned_eval_many (const ade::TensT& roots,
-	age::_GENERATED_DTYPE dtype);
+	age::_GENERATED_DTYPE dtype,
+	const std::vector<std::shared_ptr<char>>* dests = nullptr,
+	const std::function<void(size_t)>& on_done = nullptr);
 
 /// Statistics of the most recent planned_eval on this thread
 const PlanStats& last_plan_stats (void);

@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -314,6 +315,7 @@ struct PNode
 	int uses_ = 0;
 	bool counted_ = false;
 	std::shared_ptr<char> data_;   // device result once computed
+	std::shared_ptr<char> dest_;   // where the caller wants the result written, if anywhere
 	// cost of the fully inlined elementwise form
 	int need_insns_ = 0;
 	int need_inputs_ = 0;
@@ -1066,13 +1068,24 @@ struct Plan
 		std::fprintf(stderr, "[plan] %s\n", text.c_str());
 	}
 
+	/// Storage for the result of n: the caller's destination when the node
+	/// is a root that was given one, a fresh block otherwise
+	static std::shared_ptr<char> out_buffer (PNode* n)
+	{
+		if (nullptr != n->dest_)
+		{
+			return n->dest_;
+		}
+		return device::alloc(n->shape_.n_elems() * age::type_size(n->dtype_));
+	}
+
 	void run_program (Program& prog, PNode* n)
 	{
 		if (tracing())
 		{
 			trace_program(prog, n);
 		}
-		n->data_ = device::alloc(n->shape_.n_elems() * age::type_size(n->dtype_));
+		n->data_ = out_buffer(n);
 		uint64_t outshape[R];
 		std::copy(n->shape_.begin(), n->shape_.end(), outshape);
 		device::check(llo_cuda_elementwise(device::ctx(), (int) n->dtype_,
@@ -1156,7 +1169,7 @@ struct Plan
 			argdata.push_back(DataArg{a.node_->data_, a.node_->shape_,
 				a.coorder_, a.push_});
 		}
-		n->data_ = device::alloc(n->shape_.n_elems() * age::type_size(n->dtype_));
+		n->data_ = out_buffer(n);
 		age::op_exec((age::_GENERATED_OPCODE) n->opcode_, n->dtype_,
 			n->data_.get(), n->shape_, argdata);
 	}
@@ -1215,7 +1228,7 @@ struct Plan
 		}
 		uint64_t outshape[R];
 		std::copy(n->shape_.begin(), n->shape_.end(), outshape);
-		n->data_ = device::alloc(n->shape_.n_elems() * age::type_size(n->dtype_));
+		n->data_ = out_buffer(n);
 		int mode = 0 != get_option("sequential_reduce") ?
 			LLO_REDUCE_SEQUENTIAL : LLO_REDUCE_TREE;
 		device::check(llo_cuda_reduce_view(device::ctx(), n->opcode_,
@@ -1338,7 +1351,7 @@ struct Plan
 		evaluate(fa.node_);
 		evaluate(fb.node_);
 		size_t esize = age::type_size(n->dtype_);
-		n->data_ = device::alloc(n->shape_.n_elems() * esize);
+		n->data_ = out_buffer(n);
 		const char* A = fa.node_->data_.get() + sa.offset * (int64_t) esize;
 		const char* B = fb.node_->data_.get() + sb.offset * (int64_t) esize;
 		int precision = (age::FLOAT == n->dtype_ && 0 != get_option("tf32x3")) ?
@@ -1367,7 +1380,8 @@ static thread_local PlanStats last_stats;
 }
 
 std::vector<GenericData> planned_eval_many (const ade::TensT& roots,
-	age::_GENERATED_DTYPE dtype)
+	age::_GENERATED_DTYPE dtype, const std::vector<std::shared_ptr<char>>* dests,
+	const std::function<void(size_t)>& on_done)
 {
 	// one plan for every root: sub-graphs the roots share (the forward pass
 	// under a set of gradients) are computed once
@@ -1381,15 +1395,49 @@ std::vector<GenericData> planned_eval_many (const ade::TensT& roots,
 	{
 		plan.count_uses(top);
 	}
-	std::vector<GenericData> outs;
-	for (PNode* top : tops)
+	if (nullptr != dests)
 	{
+		if (dests->size() != roots.size())
+		{
+			logs::fatalf("cannot evaluate %d roots into %d destinations",
+				(int) roots.size(), (int) dests->size());
+		}
+		// a root that computes (elementwise program, reduction, GEMM, generic
+		// functor) writes straight into its destination; leaves, views,
+		// constants and roots that share a node are copied there afterwards
+		for (size_t i = 0; i < tops.size(); ++i)
+		{
+			PNode* top = tops[i];
+			bool computes = Kind::ELEM == top->kind_ || Kind::REDUCE == top->kind_ ||
+				Kind::GENERIC == top->kind_;
+			if (computes && nullptr == top->dest_ && nullptr == top->data_ &&
+				nullptr != (*dests)[i])
+			{
+				top->dest_ = (*dests)[i];
+			}
+		}
+	}
+	std::vector<GenericData> outs;
+	for (size_t i = 0; i < tops.size(); ++i)
+	{
+		PNode* top = tops[i];
 		plan.evaluate(top);
 		GenericData out;
 		out.shape_ = top->shape_;
 		out.dtype_ = dtype;
 		out.device_ = top->data_;
+		if (nullptr != dests && nullptr != (*dests)[i] &&
+			top->data_.get() != (*dests)[i].get())
+		{
+			device::check(llo_cuda_d2d(device::ctx(), (*dests)[i].get(),
+				top->data_.get(), out.nbytes()));
+			out.device_ = (*dests)[i];
+		}
 		outs.push_back(out);
+		if (on_done)
+		{
+			on_done(i);
+		}
 	}
 	last_stats = plan.stats_;
 	return outs;
@@ -1397,7 +1445,7 @@ std::vector<GenericData> planned_eval_many (const ade::TensT& roots,
 
 GenericData planned_eval (ade::TensptrT root, age::_GENERATED_DTYPE dtype)
 {
-	return planned_eval_many(ade::TensT{root}, dtype)[0];
+	return planned_eval_many(ade::TensT{root}, dtype, nullptr, nullptr)[0];
 }
 
 const PlanStats& last_plan_stats (void)

@@ -1,0 +1,253 @@
+#include <unordered_set>
+
+#include "llo/plan.hpp"
+#include "llo/sharded.hpp"
+#include "llo/zprune.hpp"
+
+#ifdef LLO_SHARDED_HPP
+
+namespace llo
+{
+
+ShardPlan::ShardPlan (size_t batch, size_t world) : batch_(batch), world_(world)
+{
+	if (world < 1 || batch < world)
+	{
+		logs::fatalf("cannot shard %d rows over %d ranks", (int) batch, (int) world);
+	}
+}
+
+std::pair<size_t,size_t> ShardPlan::bounds (size_t rank) const
+{
+	if (rank >= world_)
+	{
+		logs::fatalf("rank %d outside [0, %d)", (int) rank, (int) world_);
+	}
+	size_t base = batch_ / world_;
+	size_t extra = batch_ % world_;
+	size_t lo = rank * base + std::min(rank, extra);
+	return {lo, lo + base + (rank < extra ? 1 : 0)};
+}
+
+GradientPack::GradientPack (const std::vector<ade::Shape>& shapes,
+	age::_GENERATED_DTYPE dtype) : dtype_(dtype), shapes_(shapes)
+{
+	size_t align = std::max<size_t>(1, 16 / age::type_size(dtype));
+	for (const ade::Shape& shape : shapes)
+	{
+		size_t n = shape.n_elems();
+		offsets_.push_back(count_);
+		sizes_.push_back(n);
+		count_ += (n + align - 1) / align * align;
+	}
+}
+
+/// true when `needle` is reachable from `root` (other than root itself)
+static bool reaches (ade::iTensor* root, const std::unordered_set<ade::iTensor*>& needles)
+{
+	std::unordered_set<ade::iTensor*> seen;
+	std::vector<ade::iTensor*> todo;
+	auto push_children = [&](ade::iTensor* t)
+	{
+		if (auto f = dynamic_cast<ade::iFunctor*>(t))
+		{
+			for (const ade::MappedTensor& child : f->get_children())
+			{
+				todo.push_back(child.get_tensor().get());
+			}
+		}
+	};
+	push_children(root);
+	while (false == todo.empty())
+	{
+		ade::iTensor* t = todo.back();
+		todo.pop_back();
+		if (false == seen.emplace(t).second)
+		{
+			continue;
+		}
+		if (needles.end() != needles.find(t))
+		{
+			return true;
+		}
+		push_children(t);
+	}
+	return false;
+}
+
+ShardedEvaluator::ShardedEvaluator (ade::TensptrT loss, ade::TensT params,
+	ShardedOptions options) : params_(params), options_(options)
+{
+	ade::TensT roots = {loss};
+	for (const ade::TensptrT& param : params)
+	{
+		roots.push_back(derive(loss, param.get()));
+	}
+	if (0 != options.passes_)
+	{
+		// the loss is rewritten together with the gradients so that they keep
+		// sharing the forward pass
+		roots = optimize(roots, options.passes_, &report_);
+	}
+	roots_ = roots;
+	// folding a gradient in place while later roots are still computed is only
+	// safe if no later root reads it
+	std::unordered_set<ade::iTensor*> grads;
+	for (size_t i = 1; i < roots_.size(); ++i)
+	{
+		if (nullptr != dynamic_cast<ade::iFunctor*>(roots_[i].get()))
+		{
+			grads.emplace(roots_[i].get());
+		}
+	}
+	for (size_t i = 0; i < roots_.size() && independent_; ++i)
+	{
+		independent_ = false == reaches(roots_[i].get(), grads);
+	}
+}
+
+ShardedEvaluator::Layout& ShardedEvaluator::layout (
+	age::_GENERATED_DTYPE dtype, bool with_loss)
+{
+	std::pair<int,bool> key((int) dtype, with_loss);
+	for (size_t i = 0; i < layout_keys_.size(); ++i)
+	{
+		if (layout_keys_[i] == key)
+		{
+			return layouts_[i];
+		}
+	}
+	std::vector<ade::Shape> shapes;
+	if (with_loss)
+	{
+		shapes.push_back(roots_[0]->shape());
+	}
+	for (const ade::TensptrT& param : params_)
+	{
+		shapes.push_back(param->shape());
+	}
+	Layout lay;
+	lay.pack_ = GradientPack(shapes, dtype);
+	lay.buffer_ = device::alloc(lay.pack_.nbytes());
+	// padding between slots takes part in the fold: keep it defined
+	device::check(llo_cuda_memset(device::ctx(), lay.buffer_.get(), 0,
+		lay.pack_.nbytes()));
+	size_t esize = age::type_size(dtype);
+	for (size_t offset : lay.pack_.offsets_)
+	{
+		// aliasing pointers: the slot keeps the buffer alive
+		lay.slots_.push_back(std::shared_ptr<char>(lay.buffer_,
+			lay.buffer_.get() + offset * esize));
+	}
+	layout_keys_.push_back(key);
+	layouts_.push_back(lay);
+	return layouts_.back();
+}
+
+const GradientPack& ShardedEvaluator::pack (age::_GENERATED_DTYPE dtype,
+	bool with_loss)
+{
+	return layout(dtype, with_loss).pack_;
+}
+
+std::shared_ptr<char> ShardedEvaluator::grad_eval_device (
+	age::_GENERATED_DTYPE dtype, bool with_loss)
+{
+	Layout& lay = layout(dtype, with_loss);
+	llo_cuda_ctx* ctx = device::ctx();
+	size_t esize = age::type_size(dtype);
+	size_t nparams = params_.size();
+	bool many = false == options_.solo_ && llo_cuda_comm_size(ctx) > 1;
+	bool overlap = many && options_.overlap_ && false == options_.ordered_ &&
+		independent_ && nparams > 0;
+
+	// evaluation order = backward order: the loss, then the gradients of the
+	// LAST parameters first (they are complete first, the derivative chain
+	// reaches the first layer last)
+	ade::TensT roots;
+	std::vector<std::shared_ptr<char>> dests;
+	std::vector<size_t> slot_of;
+	if (with_loss)
+	{
+		roots.push_back(roots_[0]);
+		dests.push_back(lay.slots_[0]);
+		slot_of.push_back(0);
+	}
+	for (size_t k = nparams; k-- > 0;)
+	{
+		size_t slot = k + (with_loss ? 1 : 0);
+		roots.push_back(roots_[1 + k]);
+		dests.push_back(lay.slots_[slot]);
+		slot_of.push_back(slot);
+	}
+	// Buckets: slots are contiguous in the buffer, so a run of roots that is
+	// complete folds with one call.  Two gradients (weights + bias of a
+	// layer) per bucket keeps the calls few; the loss joins the last bucket.
+	size_t first_grad = with_loss ? 1 : 0;
+	std::function<void(size_t)> on_done = nullptr;
+	if (overlap)
+	{
+		on_done = [&](size_t i)
+		{
+			if (i < first_grad)
+			{
+				return; // the loss travels with the last bucket
+			}
+			size_t g = i - first_grad;       // g-th gradient in backward order
+			bool last = g + 1 == nparams;
+			if (0 == g % 2 && false == last)
+			{
+				return; // first of a pair: wait for its partner
+			}
+			// backward order walks the slots downwards: this root has the
+			// lowest slot of its bucket, the bucket's first root the highest
+			size_t lo_slot = slot_of[i];
+			size_t hi_slot = slot_of[i - g % 2];
+			if (last && with_loss)
+			{
+				lo_slot = 0;
+			}
+			size_t lo = lay.pack_.offsets_[lo_slot];
+			size_t hi = hi_slot + 1 < lay.pack_.offsets_.size() ?
+				lay.pack_.offsets_[hi_slot + 1] : lay.pack_.count_;
+			device::check(llo_cuda_allreduce_async(ctx,
+				lay.buffer_.get() + lo * esize, hi - lo, (int) dtype, age::SUM));
+		};
+	}
+	planned_eval_many(roots, dtype, &dests, on_done);
+	if (overlap)
+	{
+		device::check(llo_cuda_comm_join(ctx));
+	}
+	else if (many)
+	{
+		device::check(llo_cuda_allreduce(ctx, lay.buffer_.get(),
+			lay.pack_.count_, (int) dtype, age::SUM,
+			options_.ordered_ ? LLO_ALLREDUCE_ORDERED : LLO_ALLREDUCE_FAST));
+	}
+	return lay.buffer_;
+}
+
+std::vector<GenericData> ShardedEvaluator::grad_eval (
+	age::_GENERATED_DTYPE dtype, bool with_loss)
+{
+	std::shared_ptr<char> buffer = grad_eval_device(dtype, with_loss);
+	const GradientPack& pk = pack(dtype, with_loss);
+	size_t esize = age::type_size(dtype);
+	std::vector<GenericData> outs;
+	for (size_t i = 0; i < pk.shapes_.size(); ++i)
+	{
+		GenericData out;
+		out.shape_ = pk.shapes_[i];
+		out.dtype_ = dtype;
+		out.device_ = std::shared_ptr<char>(buffer,
+			buffer.get() + pk.offsets_[i] * esize);
+		out.fetch();
+		outs.push_back(out);
+	}
+	return outs;
+}
+
+}
+
+#endif

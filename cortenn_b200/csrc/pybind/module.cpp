@@ -200,6 +200,9 @@ struct DeviceBuffer
 	DeviceBuffer (size_t nbytes) :
 		nbytes_(nbytes), data_(llo::device::alloc(nbytes)) {}
 
+	DeviceBuffer (std::shared_ptr<char> data, size_t nbytes) :
+		nbytes_(nbytes), data_(data) {}
+
 	size_t nbytes_;
 
 	std::shared_ptr<char> data_;
@@ -527,6 +530,79 @@ PYBIND11_MODULE(_C, m)
 			}, "fold the buffer in place over every rank of the context's "
 			"communicator (K8)",
 			py::arg("dtype"), py::arg("op") = "SUM", py::arg("ordered") = false);
+
+	py::class_<llo::ShardedEvaluator>(llo_m, "ShardedEvaluator")
+		.def(py::init([](T loss, std::vector<T> params, unsigned passes,
+			bool ordered, bool overlap, bool solo)
+			{
+				llo::ShardedOptions opts;
+				opts.passes_ = passes;
+				opts.ordered_ = ordered;
+				opts.overlap_ = overlap;
+				opts.solo_ = solo;
+				return new llo::ShardedEvaluator(loss, params, opts);
+			}), "gradient evaluation of `loss` w.r.t. `params`, summed over the "
+			"ranks of the communicator (llo/sharded.hpp)",
+			py::arg("loss"), py::arg("params"),
+			py::arg("passes") = (unsigned) llo::OPT_ALL, py::arg("ordered") = false,
+			py::arg("overlap") = true, py::arg("solo") = false)
+		.def("grad_eval_device", [](llo::ShardedEvaluator& self, py::dtype dtype,
+			bool with_loss)
+			{
+				age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);
+				const llo::GradientPack& pk = self.pack(ctype, with_loss);
+				return pyllo::DeviceBuffer(self.grad_eval_device(ctype, with_loss),
+					pk.nbytes());
+			}, "one gradient evaluation; the packed, summed gradients stay in HBM "
+			"(the buffer is reused by the next call)",
+			py::arg("dtype"), py::arg("with_loss") = false)
+		.def("grad_eval", [](llo::ShardedEvaluator& self, py::dtype dtype,
+			bool with_loss)
+			{
+				age::_GENERATED_DTYPE ctype = pyllo::eval_dtype(dtype);
+				std::vector<llo::GenericData> datas = self.grad_eval(ctype, with_loss);
+				std::vector<py::array> outs;
+				for (llo::GenericData& d : datas)
+				{
+					outs.push_back(pyllo::wrap_host(dtype,
+						pyllo::c2pshape(d.shape_), d.data_));
+				}
+				return outs;
+			}, py::arg("dtype"), py::arg("with_loss") = false)
+		.def("pack_layout", [](llo::ShardedEvaluator& self, py::dtype dtype,
+			bool with_loss)
+			{
+				const llo::GradientPack& pk = self.pack(pyllo::eval_dtype(dtype), with_loss);
+				py::dict out;
+				out["offsets"] = pk.offsets_;
+				out["sizes"] = pk.sizes_;
+				out["count"] = pk.count_;
+				std::vector<std::vector<py::ssize_t>> shapes;
+				for (const ade::Shape& sh : pk.shapes_)
+				{
+					shapes.push_back(pyllo::c2pshape(sh));
+				}
+				out["shapes"] = shapes;
+				return out;
+			}, py::arg("dtype"), py::arg("with_loss") = false)
+		.def("roots", [](llo::ShardedEvaluator& self) { return self.roots_; })
+		.def("opt_report", [](llo::ShardedEvaluator& self)
+			{
+				py::dict rep;
+				rep["functors_before"] = self.report_.functors_before_;
+				rep["functors_after"] = self.report_.functors_after_;
+				rep["one_mul"] = self.report_.one_mul_;
+				rep["zero_add"] = self.report_.zero_add_;
+				rep["pow_one"] = self.report_.pow_one_;
+				rep["single"] = self.report_.single_;
+				rep["shared"] = self.report_.shared_;
+				rep["div_cancel"] = self.report_.div_cancel_;
+				return rep;
+			});
+	llo_m.def("shard_bounds", [](size_t batch, size_t world, size_t rank)
+		{
+			return llo::ShardPlan(batch, world).bounds(rank);
+		}, "[first, last) rows of `rank` when `batch` rows are split over `world` ranks");
 
 	llo_m.def("comm_unique_id", []()
 		{

@@ -91,18 +91,29 @@ class GradientPack:
 
 
 class DeviceBackend:
-    """Product backend: llo evaluator on this rank's B200 + NCCL through the
-    C-ABI communicator of the evaluator's context."""
+    """Product backend: a binding of llo::ShardedEvaluator (csrc/host/llo/sharded.hpp).
+    Deriving, the optimize passes, the packed layout, writing every gradient straight
+    into its slot and the bucketed, overlapped NCCL fold all happen in C++; this class
+    only keeps one evaluator per (loss, params) and hands numpy views back."""
 
-    def __init__(self, ordered=False):
+    native = True
+
+    def __init__(self, ordered=False, overlap=True, solo_rank=False):
         from . import llo
         if not llo.available():
             raise RuntimeError("batch-sharded evaluation needs a B200; there is no CPU fallback")
         self.llo = llo
         self.ordered = bool(ordered)
-        self._buffers = {}
+        # LLO_SHARD_OVERLAP=0: one fold after the last gradient (A/B runs)
+        self.overlap = bool(overlap) and os.environ.get("LLO_SHARD_OVERLAP", "1") != "0"
+        self.solo_rank = bool(solo_rank)
+        self._evaluators = {}
 
     def init_comm(self, rank, world, exchange):
+        if self.solo_rank:
+            if world != 1:
+                raise ValueError("the solo backend evaluates on one rank")
+            return
         if self.llo.comm_size() == world and self.llo.comm_rank() == rank and world > 1:
             return
         if world == 1:
@@ -112,48 +123,24 @@ class DeviceBackend:
         ident = exchange(ident)
         self.llo.comm_init(rank, world, ident)
 
-    def evaluate_many(self, roots, dtype):
-        return self.llo.evaluate_device_many(roots, np.dtype(dtype))
-
-    def reduce_packed(self, results, pack):
-        """pack device results -> flat buffer -> allreduce; returns the buffer"""
-        buf = self._buffers.get(pack.nbytes)
-        if buf is None:
-            buf = self.llo.DeviceBuffer(pack.nbytes)
-            self._buffers[pack.nbytes] = buf
-        itemsize = pack.dtype.itemsize
-        for off, res in zip(pack.offsets, results):
-            buf.store(off * itemsize, res)
-        buf.allreduce(pack.dtype, "SUM", self.ordered)
-        return buf
+    def evaluator(self, loss, params, passes):
+        key = (id(loss), tuple(id(p) for p in params), passes)
+        if key not in self._evaluators:
+            ev = self.llo.ShardedEvaluator(loss, list(params), passes, self.ordered, self.overlap,
+                                           self.solo_rank)
+            self._evaluators[key] = (loss, list(params), ev)     # keeps the ids alive
+        return self._evaluators[key][2]
 
     def solo(self):
-        return SoloDeviceBackend()
+        """this rank alone on its own GPU, leaving the ranks' communicator untouched: the
+        single-GPU evaluation a multi-rank run checks its agreed gradient against"""
+        return DeviceBackend(ordered=False, overlap=False, solo_rank=True)
 
     def to_host(self, buf, pack):
         return pack.unpack(buf.numpy(pack.dtype, 0, pack.count))
 
     def scalar(self, buf, pack, index):
         return buf.numpy(pack.dtype, pack.offsets[index] * pack.dtype.itemsize, 1)[0]
-
-
-class SoloDeviceBackend(DeviceBackend):
-    """This rank alone on its own GPU, leaving the ranks' communicator untouched: the
-    single-GPU evaluation a multi-rank run checks its agreed gradient against"""
-
-    def init_comm(self, rank, world, exchange):
-        if world != 1:
-            raise ValueError("the solo backend evaluates on one rank")
-
-    def reduce_packed(self, results, pack):
-        buf = self._buffers.get(pack.nbytes)
-        if buf is None:
-            buf = self.llo.DeviceBuffer(pack.nbytes)
-            self._buffers[pack.nbytes] = buf
-        itemsize = pack.dtype.itemsize
-        for off, res in zip(pack.offsets, results):
-            buf.store(off * itemsize, res)
-        return buf
 
 
 def _default_exchange(ident):
@@ -198,8 +185,19 @@ class BatchShardedExecutor:
     def local_rows(self):
         return self.plan.rows(self.rank)
 
+    def _native(self):
+        return getattr(self.backend, "native", False)
+
+    def _passes(self):
+        from . import llo
+        return llo.OPT_ALL if self.passes is None else int(self.passes)
+
     def derive(self, loss, params):
         """gradient graphs of `loss` w.r.t. every parameter (cached per loss)"""
+        if self._native():
+            ev = self.backend.evaluator(loss, params, self._passes())
+            self.opt_report = ev.opt_report()
+            return ev.roots()[1:]
         from . import llo
         key = (id(loss), tuple(id(p) for p in params))
         if key not in self._derived:
@@ -217,6 +215,14 @@ class BatchShardedExecutor:
     def grad_eval_device(self, loss, params, dtype, with_loss=False):
         """one gradient evaluation; returns (buffer, pack) with the summed
         gradients (and the summed loss first when with_loss) in HBM"""
+        if self._native():
+            ev = self.backend.evaluator(loss, params, self._passes())
+            if self.opt_report is None:
+                self.opt_report = ev.opt_report()
+            shapes = [self._shape(p) for p in params]
+            if with_loss:
+                shapes = [()] + shapes
+            return ev.grad_eval_device(np.dtype(dtype), with_loss), GradientPack(shapes, dtype)
         roots = list(self.derive(loss, params))
         shapes = [self._shape(p) for p in params]
         if with_loss:
