@@ -340,7 +340,10 @@ int make_ready (llo_cuda_ctx* ctx, Scratch& scratch, const T*& base,
 /// PERSIST: the kernel is persistent (one CTA per SM walking work units,
 /// operand pipeline kept full across units) and takes the tail-split plan
 /// (full_tiles / tail_splits / part) instead of the (tile, split) grid.
-template <typename T, int BM, int BN, int BK, bool PERSIST = false, typename Launch>
+/// DUAL: CTAs per SM of the kernel variant whose operands are both [k][row]
+/// tiles (the fp32 one fits two; every other variant runs one)
+template <typename T, int BM, int BN, int BK, bool PERSIST = false, int DUAL = 1,
+	typename Launch>
 int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 	const T* B, bool& handled, int vec_nc, int vec_kc, Launch launch)
 {
@@ -457,7 +460,9 @@ int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 		// times: rounds x (k-tiles per unit + ~2 for the epilogue and the
 		// pipeline bubble) + 2 for the fold pass.  With fewer tiles than SMs
 		// this is plain split-K.
-		uint64_t sms = (uint64_t) ctx->sm_count;
+		// (co-resident CTAs share the SM: a round of `sms` units takes as
+		// long whether one or two CTAs per SM work through it)
+		uint64_t sms = (uint64_t) ctx->sm_count * ((false == ak && false == bk) ? DUAL : 1);
 		uint64_t rest = tiles % sms;
 		uint32_t splits = 1;
 		if (0 != rest)
@@ -520,19 +525,58 @@ int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 	// the fold pass.
 	uint32_t splits = 1;
 	{
+		// Measured on the dW shapes of the MLP (round 2, LLO_GEMM_SPLITS sweep,
+		// 1024x1024x8192: 2 splits 0.363 ms, 9 splits 0.327, 16 splits 0.324;
+		// 784x1024x65536: 5 splits 2.15 ms, 16 splits 2.01): an SM works through
+		// its CTAs at the same rate whether one or two are resident, so the time
+		// is (CTAs per SM, rounded up) x (k-tiles per CTA + ~1 of fill that the
+		// co-resident CTA does not hide), plus the fold pass (~0.35 k-tile times
+		// per split for a 1024 x 1024 output).  Edge tiles whose warps lie
+		// outside C skip their math (sgemm.cu) and count for the live fraction.
 		uint64_t sms = (uint64_t) ctx->sm_count;
+		uint64_t live_m = ((p.M % BM) + 63) / 64;     // live 64-row warp halves of the last tile row
+		uint64_t live_n = ((p.N % BN) + 31) / 32;     // live 32-column warp quarters of the last tile column
+		uint64_t tiles_x8 = 0;                        // tiles in eighths of a tile's warps
+		{
+			uint64_t full_m = p.M / BM, full_n = p.N / BN;
+			tiles_x8 = full_m * full_n * 8 + (0 != p.M % BM ? full_n * live_m * 4 : 0) +
+				(0 != p.N % BN ? full_m * live_n * 2 : 0) +
+				((0 != p.M % BM && 0 != p.N % BN) ? live_m * live_n : 0);
+			if (4 != sizeof(T))
+			{
+				tiles_x8 = tiles * 8;                 // (only the fp32 kernel skips dead warps)
+			}
+		}
+		uint64_t fold_x100 = 35 * (p.M * p.N) / (1024 * 1024) + 1;
+		// Three regimes (all in hundredths of a k-tile time):
+		//  * every CTA is resident at once (<= 2 per SM): the SMs holding two
+		//    take twice as long as those holding one;
+		//  * more CTAs, all alike: they finish in waves, CTAs per SM rounded up;
+		//  * more CTAs, some of them short (edge tiles): the short ones break
+		//    the waves and the hardware scheduler balances the SMs; a quarter of
+		//    a CTA is left over as imbalance
 		auto cost = [&] (uint64_t cand) -> uint64_t
 		{
-			uint64_t waves = (tiles * cand + sms - 1) / sms;
 			uint64_t per = (ktiles + cand - 1) / cand;
-			return waves * (per + 3) + (cand > 1 ? 1 : 0);
+			uint64_t ctas = tiles * cand;
+			uint64_t fold = cand > 1 ? cand * fold_x100 : 0;
+			if (ctas <= 2 * sms)
+			{
+				return (ctas > sms ? 2 : 1) * (per + 1) * 100 + fold;
+			}
+			if (tiles_x8 == tiles * 8)
+			{
+				return (ctas + sms - 1) / sms * (per + 1) * 100 + fold;
+			}
+			return tiles_x8 * cand * (ktiles * 100 / cand + 100) / (8 * sms) +
+				25 * (per + 1) + fold;
 		};
 		uint64_t best = cost(1);
-		uint64_t most = std::min<uint64_t>(ktiles / 4, 64);
+		uint64_t most = std::min<uint64_t>(ktiles / 4, 32);
 		for (uint64_t cand = 2; cand <= most; ++cand)
 		{
 			uint64_t c = cost(cand);
-			if (c * 100 < best * 95) // worth it only for a clear gain
+			if (c * 100 < best * 99)
 			{
 				best = c;
 				splits = (uint32_t) cand;

@@ -162,6 +162,19 @@ struct Frag
 	float4 v[2][KC ? 8 : 2];
 };
 
+// Two CTAs per SM when both operands are [k][row] tiles: that variant needs
+// 127 registers, so with a 3-stage ring (100 KB) two CTAs fit and every
+// scheduler has 4 warps to pick from instead of 2.
+template <bool AK, bool BKC>
+struct GridShape
+{
+	static constexpr int CTAS = (AK || BKC) ? 1 : 2;
+	static constexpr int ST = (AK || BKC) ? STAGES : 3;
+	static constexpr uint32_t AHEAD = ST - 2;
+	static constexpr size_t SMEM = 1024 /* alignment slack */ +
+		(size_t) ST * STAGE_BYTES + TAIL_PAD + 2 * ST * sizeof(uint64_t);
+};
+
 template <bool AK, bool BKC>
 __global__ void __launch_bounds__(THREADS, 1)
 sgemm_persist_kernel (const __grid_constant__ CUtensorMap map_a,
@@ -180,7 +193,8 @@ sgemm_persist_kernel (const __grid_constant__ CUtensorMap map_a,
 	uint64_t* full = (uint64_t*) (smem + (size_t) STAGES * STAGE_BYTES + TAIL_PAD);
 	uint64_t* empty = full + STAGES;
 
-	// Persistent: one CTA per SM walks work units.  Units [0, full_tiles)
+	// Persistent: one CTA per SM walks work units (two CTAs per SM with a
+	// 3-stage ring measured slower: 8192x1024x784 49.5 -> 44.8 TFLOP/s).  Units [0, full_tiles)
 	// are whole tiles; the others are k ranges of the tail tiles (see
 	// GemmArgs).  The operand pipeline runs across unit boundaries: while a
 	// unit's last k-tiles are multiplied and its outputs stored, the TMA
@@ -567,19 +581,6 @@ sgemm_persist_kernel (const __grid_constant__ CUtensorMap map_a,
 
 // ---- one CTA per (tile, split): the hardware hands tiles to SMs -----------------
 
-// Two CTAs per SM when both operands are [k][row] tiles: that variant needs
-// 127 registers, so with a 3-stage ring (100 KB) two CTAs fit and every
-// scheduler has 4 warps to pick from instead of 2.
-template <bool AK, bool BKC>
-struct GridShape
-{
-	static constexpr int CTAS = (AK || BKC) ? 1 : 2;
-	static constexpr int ST = (AK || BKC) ? STAGES : 3;
-	static constexpr uint32_t AHEAD = ST - 2;
-	static constexpr size_t SMEM = 1024 /* alignment slack */ +
-		(size_t) ST * STAGE_BYTES + TAIL_PAD + 2 * ST * sizeof(uint64_t);
-};
-
 template <bool AK, bool BKC>
 __global__ void __launch_bounds__(THREADS, GridShape<AK,BKC>::CTAS)
 sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
@@ -907,13 +908,14 @@ template <bool AK, bool BKC>
 int launch_persist (llo_cuda_ctx* ctx, const CUtensorMap& ma,
 	const CUtensorMap& mb, const SgemmArgs& args, uint32_t splits)
 {
+	constexpr size_t smem = SMEM_BYTES;
 	LLO_CUDA_TRY(cudaFuncSetAttribute(sgemm_persist_kernel<AK,BKC>,
-		cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM_BYTES));
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	(void) splits;
 	uint64_t units = (uint64_t) args.full_tiles +
 		((uint64_t) args.tiles_m * args.tiles_n - args.full_tiles) * args.tail_splits;
 	unsigned grid = (unsigned) std::min<uint64_t>(units, (uint64_t) ctx->sm_count);
-	sgemm_persist_kernel<AK,BKC><<<grid, THREADS, SMEM_BYTES,
+	sgemm_persist_kernel<AK,BKC><<<grid, THREADS, smem,
 		ctx->stream>>>(ma, mb, args);
 	return launched(ctx, "sgemm_persist_kernel");
 }
@@ -969,7 +971,7 @@ int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p, float* C,
 	}
 	if (persist)
 	{
-		return tma::drive<float,BM,BN,BK,true>(ctx, p, C, A, B, handled, 4, 2,
+		return tma::drive<float,BM,BN,BK,true,1>(ctx, p, C, A, B, handled, 4, 2,
 			[ctx] (bool ak, bool bk, const CUtensorMap& ma, const CUtensorMap& mb,
 				const SgemmArgs& args, uint32_t splits) -> int
 			{
@@ -982,7 +984,7 @@ int sgemm_launch (llo_cuda_ctx* ctx, const GemmParams& p, float* C,
 					launch_persist<false,false>(ctx, ma, mb, args, splits);
 			});
 	}
-	return tma::drive<float,BM,BN,BK,false>(ctx, p, C, A, B, handled, 4, 2,
+	return tma::drive<float,BM,BN,BK,false,2>(ctx, p, C, A, B, handled, 4, 2,
 		[ctx] (bool ak, bool bk, const CUtensorMap& ma, const CUtensorMap& mb,
 			const SgemmArgs& args, uint32_t splits) -> int
 		{
