@@ -75,6 +75,7 @@ EXPORTS = {
     "llo_cuda_event_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "llo_cuda_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "llo_cuda_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
+    "llo_cuda_wait_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "llo_cuda_sync": (C.c_int, [C.c_void_p]),
     "llo_cuda_launch_count": (C.c_uint64, [C.c_void_p]),
     "llo_cuda_event_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -342,6 +342,27 @@ int llo_cuda_d2d (llo_cuda_ctx* ctx, void* dst, const void* src, size_t bytes)
 	return LLO_OK;
 }
 
+int llo_cuda_wait_stream (llo_cuda_ctx* ctx, void* cuda_stream)
+{
+	// work queued on the context's stream from here on starts after
+	// everything queued on `cuda_stream` so far has finished
+	cudaStream_t other = (cudaStream_t) cuda_stream;
+	if (other == ctx->stream)
+	{
+		return LLO_OK;
+	}
+	cudaEvent_t ev;
+	LLO_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+	cudaError_t err = cudaEventRecord(ev, other);
+	if (cudaSuccess == err)
+	{
+		err = cudaStreamWaitEvent(ctx->stream, ev, 0);
+	}
+	cudaEventDestroy(ev);
+	LLO_CUDA_TRY(err);
+	return LLO_OK;
+}
+
 int llo_cuda_memset (llo_cuda_ctx* ctx, void* dst, int byte, size_t bytes)
 {
 	LLO_CUDA_TRY(cudaMemsetAsync(dst, byte, bytes, ctx->stream));

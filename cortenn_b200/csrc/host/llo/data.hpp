@@ -138,6 +138,14 @@ struct Variable final : public ade::iLeaf
 	/// been waited for.
 	void assign_async (GenericRef data);
 
+	/// Same checks and effect as `= data` for elements that already live in
+	/// DEVICE memory (another library's tensor handed over through
+	/// __cuda_array_interface__ / DLPack): one device-to-device copy into a
+	/// fresh mirror, no host bounce.  The copy is ordered on the evaluator's
+	/// stream; the caller orders the producer before it (llo_cuda_wait_stream).
+	void assign_device (const void* device_data, ade::Shape shape,
+		age::_GENERATED_DTYPE dtype);
+
 	/// Implementation of iTensor
 	const ade::Shape& shape (void) const override
 	{

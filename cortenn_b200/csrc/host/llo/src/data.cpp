@@ -340,6 +340,30 @@ void Variable::assign_async (GenericRef data)
 	host_stale_ = true;
 }
 
+void Variable::assign_device (const void* device_data, ade::Shape shape,
+	age::_GENERATED_DTYPE dtype)
+{
+	if (false == shape.compatible_after(shape_, 0))
+	{
+		logs::fatalf("cannot assign data of incompatible shaped %s to "
+			"internal data of shape %s", shape.to_string().c_str(),
+			shape_.to_string().c_str());
+	}
+	if (dtype != dtype_)
+	{
+		logs::fatalf("cannot assign data of incompatible types %s "
+			"(external) and %s (internal)",
+			age::name_type(dtype).c_str(), age::name_type(dtype_).c_str());
+	}
+	fill_.clear();
+	++version_;
+	std::shared_ptr<char> raw = device::alloc(nbytes());
+	device::check(llo_cuda_d2d(device::ctx(), raw.get(), device_data, nbytes()));
+	mirrors_.clear();
+	mirrors_.push_back(Mirror{dtype_, version_, raw});
+	host_stale_ = true;
+}
+
 void Variable::materialize (void) const
 {
 	if (host_stale_)

@@ -99,6 +99,186 @@ static age::_GENERATED_DTYPE exact_dtype (py::dtype dtype, const char* what)
 	return age::BAD_TYPE;
 }
 
+
+// ---- zero-copy device interop --------------------------------
+//
+// Results leave as __cuda_array_interface__ (version 3) and DLPack capsules;
+// leaves accept any object that offers __cuda_array_interface__ (a torch / cupy
+// CUDA tensor) and copy device-to-device.  The reference's binding only knows
+// host numpy arrays (llo/python/llo.cpp:36-147).
+
+static const char* typestr_of (age::_GENERATED_DTYPE dtype)
+{
+	switch (dtype)
+	{
+		case age::DOUBLE: return "<f8";
+		case age::FLOAT: return "<f4";
+		case age::INT8: return "|i1";
+		case age::UINT8: return "|u1";
+		case age::INT16: return "<i2";
+		case age::UINT16: return "<u2";
+		case age::INT32: return "<i4";
+		case age::UINT32: return "<u4";
+		case age::INT64: return "<i8";
+		case age::UINT64: return "<u8";
+		default: logs::fatal("cannot describe bad type");
+	}
+}
+
+static age::_GENERATED_DTYPE dtype_of_typestr (const std::string& ts)
+{
+	if (ts.size() < 3 || '>' == ts[0])
+	{
+		logs::fatalf("unsupported device array type %s", ts.c_str());
+	}
+	std::string kind = ts.substr(1);
+	if ("f8" == kind) return age::DOUBLE;
+	if ("f4" == kind) return age::FLOAT;
+	if ("i1" == kind) return age::INT8;
+	if ("u1" == kind) return age::UINT8;
+	if ("i2" == kind) return age::INT16;
+	if ("u2" == kind) return age::UINT16;
+	if ("i4" == kind) return age::INT32;
+	if ("u4" == kind) return age::UINT32;
+	if ("i8" == kind) return age::INT64;
+	if ("u8" == kind) return age::UINT64;
+	logs::fatalf("unsupported device array type %s", ts.c_str());
+}
+
+static py::dict cuda_array_interface (const std::shared_ptr<char>& data,
+	const std::vector<py::ssize_t>& pshape, age::_GENERATED_DTYPE dtype)
+{
+	py::dict out;
+	out["shape"] = py::tuple(py::cast(pshape));
+	out["typestr"] = typestr_of(dtype);
+	out["data"] = py::make_tuple((uintptr_t) data.get(), false);
+	out["version"] = 3;
+	out["strides"] = py::none();
+	// consumers order themselves behind the evaluator's stream (1 would be
+	// the legacy default stream; a real handle is passed as an integer)
+	uintptr_t stream = (uintptr_t) llo_cuda_get_stream(llo::device::ctx());
+	out["stream"] = 0 == stream ? py::object(py::int_(1)) : py::object(py::int_(stream));
+	return out;
+}
+
+// the slice of dlpack.h (v0.8) this module needs
+struct DLDevice { int32_t device_type; int32_t device_id; };
+struct DLDataType { uint8_t code; uint8_t bits; uint16_t lanes; };
+struct DLTensor
+{
+	void* data;
+	DLDevice device;
+	int32_t ndim;
+	DLDataType dtype;
+	int64_t* shape;
+	int64_t* strides;
+	uint64_t byte_offset;
+};
+struct DLManagedTensor
+{
+	DLTensor dl_tensor;
+	void* manager_ctx;
+	void (*deleter) (DLManagedTensor*);
+};
+
+struct DLOwner
+{
+	std::shared_ptr<char> data_;
+	std::vector<int64_t> shape_;
+	DLManagedTensor managed_;
+};
+
+static py::capsule dlpack_of (const std::shared_ptr<char>& data,
+	const std::vector<py::ssize_t>& pshape, age::_GENERATED_DTYPE dtype)
+{
+	// the consumer may use the memory on any stream: finish ours first
+	llo::device::check(llo_cuda_sync(llo::device::ctx()));
+	DLOwner* owner = new DLOwner();
+	owner->data_ = data;
+	owner->shape_.assign(pshape.begin(), pshape.end());
+	DLTensor& t = owner->managed_.dl_tensor;
+	t.data = data.get();
+	t.device = DLDevice{2 /* kDLCUDA */, llo_cuda_device(llo::device::ctx())};
+	t.ndim = (int32_t) owner->shape_.size();
+	bool fp = age::DOUBLE == dtype || age::FLOAT == dtype;
+	bool uns = age::UINT8 == dtype || age::UINT16 == dtype ||
+		age::UINT32 == dtype || age::UINT64 == dtype;
+	t.dtype = DLDataType{(uint8_t) (fp ? 2 : (uns ? 1 : 0)),
+		(uint8_t) (8 * age::type_size(dtype)), 1};
+	t.shape = owner->shape_.data();
+	t.strides = nullptr;
+	t.byte_offset = 0;
+	owner->managed_.manager_ctx = owner;
+	owner->managed_.deleter = [](DLManagedTensor* self)
+	{
+		delete static_cast<DLOwner*>(self->manager_ctx);
+	};
+	return py::capsule(&owner->managed_, "dltensor", [](PyObject* cap)
+	{
+		// still named "dltensor": nobody consumed it, so it is ours to free
+		if (PyCapsule_IsValid(cap, "dltensor"))
+		{
+			auto managed = static_cast<DLManagedTensor*>(
+				PyCapsule_GetPointer(cap, "dltensor"));
+			managed->deleter(managed);
+		}
+	});
+}
+
+/// A device array offered through __cuda_array_interface__
+struct DeviceArrayView
+{
+	const void* data_ = nullptr;
+	ade::Shape shape_;
+	age::_GENERATED_DTYPE dtype_ = age::BAD_TYPE;
+};
+
+static bool is_device_array (const py::object& obj)
+{
+	return py::hasattr(obj, "__cuda_array_interface__");
+}
+
+static DeviceArrayView device_array (const py::object& obj)
+{
+	py::dict cai = obj.attr("__cuda_array_interface__");
+	DeviceArrayView out;
+	std::vector<py::ssize_t> pshape = cai["shape"].cast<std::vector<py::ssize_t>>();
+	out.dtype_ = dtype_of_typestr(cai["typestr"].cast<std::string>());
+	if (cai.contains("strides") && false == cai["strides"].is_none())
+	{
+		// only dense C order is accepted (what .contiguous() gives)
+		std::vector<py::ssize_t> strides = cai["strides"].cast<std::vector<py::ssize_t>>();
+		py::ssize_t expect = (py::ssize_t) age::type_size(out.dtype_);
+		for (size_t i = pshape.size(); i-- > 0;)
+		{
+			if (pshape[i] > 1 && strides[i] != expect)
+			{
+				logs::fatal("device arrays must be C-contiguous");
+			}
+			expect *= pshape[i];
+		}
+	}
+	out.shape_ = p2cshape(pshape);
+	py::tuple data = cai["data"];
+	out.data_ = (const void*) data[0].cast<uintptr_t>();
+	// order our stream behind the producer's
+	if (cai.contains("stream") && false == cai["stream"].is_none())
+	{
+		uintptr_t stream = cai["stream"].cast<uintptr_t>();
+		llo::device::check(llo_cuda_wait_stream(llo::device::ctx(),
+			(void*) (stream <= 2 ? (uintptr_t) (2 == stream ? 2 : 0) : stream)));
+	}
+	return out;
+}
+
+static llo::VarptrT variable_from_device (py::object obj, std::string label)
+{
+	DeviceArrayView view = device_array(obj);
+	llo::VarptrT out(new llo::Variable(nullptr, view.dtype_, view.shape_, label));
+	out->assign_device(view.data_, view.shape_, view.dtype_);
+	return out;
+}
+
 static llo::VarptrT variable (py::array data, std::string label)
 {
 	py::array dense = py::array::ensure(data, py::array::c_style);
@@ -250,10 +430,16 @@ PYBIND11_MODULE(_C, m)
 	py::class_<llo::Variable,ade::iTensor,llo::VarptrT> variable(
 		llo_m, "Variable");
 	variable
-		.def("assign", [](llo::VarptrT self, py::array data)
+		.def("assign", [](llo::VarptrT self, py::object data)
 		{
-			pyllo::assign(self.get(), data);
-		}, "assign to variable")
+			if (pyllo::is_device_array(data))
+			{
+				pyllo::DeviceArrayView view = pyllo::device_array(data);
+				self->assign_device(view.data_, view.shape_, view.dtype_);
+				return;
+			}
+			pyllo::assign(self.get(), py::array::ensure(data));
+		}, "assign to variable (numpy array, or a device array: copied on the GPU)")
 		.def("assign_async", [](llo::VarptrT self, py::array data)
 		{
 			pyllo::assign_async(self.get(), data);
@@ -349,7 +535,16 @@ PYBIND11_MODULE(_C, m)
 	});
 
 	// ---- llo ----
-	llo_m.def("variable", &pyllo::variable, "create tensor variable",
+	llo_m.def("variable", [](py::object data, std::string label)
+		{
+			if (pyllo::is_device_array(data))
+			{
+				// a CUDA tensor of another library: device-to-device, no host bounce
+				return pyllo::variable_from_device(data, label);
+			}
+			return pyllo::variable(py::array::ensure(data), label);
+		}, "create tensor variable from a numpy array or from any object with "
+		"__cuda_array_interface__ (torch / cupy CUDA tensors)",
 		py::arg("data"), py::arg("label") = "");
 	llo_m.def("scalar", [](double value, std::vector<py::ssize_t> shape,
 		std::string label)
@@ -423,6 +618,21 @@ PYBIND11_MODULE(_C, m)
 			{
 				auto pshape = pyllo::c2pshape(self.data_.shape_);
 				return py::array(dtype, pshape, self.data_.fetch());
+			})
+		.def_property_readonly("__cuda_array_interface__", [](pyllo::DeviceResult& self)
+			{
+				return pyllo::cuda_array_interface(self.data_.device_,
+					pyllo::c2pshape(self.data_.shape_), self.data_.dtype_);
+			}, "the result where it lies in HBM (torch.as_tensor / cupy.asarray: no copy)")
+		.def("__dlpack__", [](pyllo::DeviceResult& self, py::object stream)
+			{
+				(void) stream;
+				return pyllo::dlpack_of(self.data_.device_,
+					pyllo::c2pshape(self.data_.shape_), self.data_.dtype_);
+			}, py::arg("stream") = py::none())
+		.def("__dlpack_device__", [](pyllo::DeviceResult&)
+			{
+				return py::make_tuple(2, llo_cuda_device(llo::device::ctx()));
 			});
 	llo_m.def("pinned_empty", [](std::vector<py::ssize_t> shape, py::dtype dtype)
 		{

@@ -110,6 +110,11 @@ int llo_cuda_h2d_async (llo_cuda_ctx* ctx, void* dst, const void* src_host, size
 int llo_cuda_d2h_async (llo_cuda_ctx* ctx, void* dst_host, const void* src, size_t bytes, void** done);
 int llo_cuda_event_sync (llo_cuda_ctx* ctx, void* event);
 int llo_cuda_memset (llo_cuda_ctx* ctx, void* dst, int byte, size_t bytes);
+/* order the context's stream behind another cudaStream_t (0 = the legacy
+ * default stream): device buffers produced by another library may then be
+ * read by calls made afterwards (zero-copy interop, llo/python/llo.cpp:36-99
+ * only knows host arrays) */
+int llo_cuda_wait_stream (llo_cuda_ctx* ctx, void* cuda_stream);
 int llo_cuda_sync (llo_cuda_ctx* ctx);
 /* number of kernels this context has launched so far (bench `gpu_launches`) */
 uint64_t llo_cuda_launch_count (llo_cuda_ctx* ctx);
