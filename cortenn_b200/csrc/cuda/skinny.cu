@@ -44,223 +44,316 @@ __device__ __forceinline__ T fma_t (T a, T b, T c)
 // E (l + 32 i) of the chunk, so it reads 16 bytes of each of its A rows per
 // step (a warp: 512 contiguous bytes per row) and one LDS.128 per column of B
 // (consecutive lanes, consecutive 16 bytes: conflict-free).  Per-lane sums run
-// in ascending k; the 32 of them fold through a fixed xor-shuffle tree.  Each
-// warp walks `groups` row groups per staged chunk to amortise the staging.
+// in ascending k; the 32 of them fold through a fixed xor-shuffle tree.
+//
+// These are bandwidth problems and what decides them is BYTES IN FLIGHT
+// (round 1: 1.0-1.5 TB/s with 32 bytes per lane outstanding).  So a warp owns
+// R = 4 rows, the loads of the next TWO steps are outstanding while a step is
+// multiplied (128-192 bytes per lane, ~100 KB per SM), and the short dimension
+// is a template argument (NN = N rounded up to 4) so that padding columns cost
+// neither registers nor FMAs and two CTAs stay resident.
 
 // k's of B staged at a time: 512 (fp32) / 256 (fp64), <= 35 KB of shared memory
 template <typename T>
 constexpr int skinny_kc (void) { return 2048 / (int) sizeof(T); }
 
-template <typename T, int R, int GROUPS>
-__global__ void __launch_bounds__(256)
-skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
-	const T* __restrict__ B, GemmParams p, int a_vec)
+/// rows a warp owns: as many as the accumulators leave registers for
+template <typename T, int NN>
+constexpr int skinny_rows_r (void)
 {
+	return (int) sizeof(T) * NN <= 48 ? 4 : ((int) sizeof(T) * NN <= 96 ? 2 : 1);
+}
+
+template <typename T, int NN>
+__global__ void __launch_bounds__(256, 2)
+skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
+	const T* __restrict__ B, GemmParams p, int a_vec, uint32_t kcap)
+{
+	constexpr int R = skinny_rows_r<T,NN>();
 	constexpr int E = 16 / (int) sizeof(T);
-	constexpr int KC = skinny_kc<T>();
-	constexpr int PITCH = KC + E;
 	using V = typename std::conditional<8 == sizeof(T), double2, float4>::type;
-	__shared__ __align__(16) T bs[SKINNY_MAX * PITCH];
+	// B is staged `kcap` k's at a time (all of it when it fits: K x NN elements),
+	// transposed: bs[n][pitch]
+	extern __shared__ __align__(16) unsigned char skinny_smem[];
+	T* bs = reinterpret_cast<T*>(skinny_smem);
+	const uint32_t pitch = kcap + E;
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	const int N = (int) p.N;
 	const uint32_t K = (uint32_t) p.K;
-	const uint64_t cta_row0 = (uint64_t) blockIdx.x * (8 * R * GROUPS);
-	T acc[GROUPS][R][SKINNY_MAX];
+	// When B fits the staging area it is staged ONCE and the CTA walks row
+	// groups blockIdx.x, + gridDim.x, ... (the launch is then persistent:
+	// staging 48 KB per 32 rows cost a third of the kernel); otherwise one
+	// row group per CTA and B in chunks.
+	const uint64_t ngroups = (p.M + 8 * R - 1) / (8 * R);
+	for (uint64_t group = blockIdx.x; group < ngroups; group += gridDim.x)
+	{
+	const uint64_t row0 = (group * 8 + warp) * R;
+	const bool live = row0 < p.M;
+	T acc[R][NN];
 #pragma unroll
-	for (int g = 0; g < GROUPS; ++g)
+	for (int r = 0; r < R; ++r)
 	{
 #pragma unroll
-		for (int r = 0; r < R; ++r)
+		for (int n = 0; n < NN; ++n)
 		{
-#pragma unroll
-			for (int n = 0; n < SKINNY_MAX; ++n)
-			{
-				acc[g][r][n] = T(0);
-			}
+			acc[r][n] = T(0);
 		}
 	}
-	for (uint32_t kc = 0; kc < K; kc += KC)
+	const T* rowp[R];
+#pragma unroll
+	for (int r = 0; r < R; ++r)
 	{
-		uint32_t len = min((uint32_t) KC, K - kc);
+		uint64_t m = row0 + r < p.M ? row0 + r : p.M - 1;
+		rowp[r] = A + (int64_t) m * p.a_rs;
+	}
+	for (uint32_t kc = 0; kc < K; kc += kcap)
+	{
+		uint32_t len = min(kcap, K - kc);
 		uint32_t padded = (len + E - 1) / E * E;
-		__syncthreads();
-		// thread t stages column t % 16 of rows t / 16, + 16, ... (zero beyond N / len)
+		if (kcap < K || group == blockIdx.x)
 		{
-			int n = threadIdx.x & (SKINNY_MAX - 1);
-			for (uint32_t k = threadIdx.x / SKINNY_MAX; k < padded; k += 256 / SKINNY_MAX)
+		__syncthreads();
+		// thread = one k: consecutive threads write consecutive words of every
+		// bs row (no bank conflicts) and read neighbouring rows of B (zero
+		// beyond N / len)
+		for (uint32_t k = threadIdx.x; k < padded; k += 256)
+		{
+			const T* brow = B + (int64_t) (kc + k) * p.b_rs;
+#pragma unroll
+			for (int n = 0; n < NN; ++n)
 			{
-				bs[n * PITCH + k] = (n < N && k < len) ?
-					__ldg(B + (int64_t) (kc + k) * p.b_rs + (int64_t) n * p.b_cs) : T(0);
+				bs[n * pitch + k] = (n < N && k < len) ?
+					__ldg(brow + (int64_t) n * p.b_cs) : T(0);
 			}
 		}
 		__syncthreads();
-#pragma unroll
-		for (int g = 0; g < GROUPS; ++g)
+		}
+		if (false == live)
 		{
-			uint64_t row0 = cta_row0 + (uint64_t) (g * 8 + warp) * R;
-			if (row0 >= p.M)
+			continue;
+		}
+		auto fetch = [&] (T (&dst)[R][E], uint32_t k0)
+		{
+			if (k0 >= padded)
 			{
-				continue;
+				return;
 			}
-			// the loads of step i + 1 are issued before the FMAs of step i
-			auto fetch = [&] (T (&dst)[R][E], uint32_t k0)
+#pragma unroll
+			for (int r = 0; r < R; ++r)
 			{
-#pragma unroll
-				for (int r = 0; r < R; ++r)
+				const T* src = rowp[r] + kc + k0;
+				if (a_vec && k0 + E <= len)
 				{
-					uint64_t m = row0 + r < p.M ? row0 + r : p.M - 1;
-					const T* src = A + (int64_t) m * p.a_rs + kc + k0;
-					if (a_vec && k0 + E <= len)
-					{
-						V v = __ldcs(reinterpret_cast<const V*>(src));
-						const T* t = reinterpret_cast<const T*>(&v);
+					V v = __ldcs(reinterpret_cast<const V*>(src));
+					const T* t = reinterpret_cast<const T*>(&v);
 #pragma unroll
-						for (int e = 0; e < E; ++e)
-						{
-							dst[r][e] = t[e];
-						}
-					}
-					else
+					for (int e = 0; e < E; ++e)
 					{
-#pragma unroll
-						for (int e = 0; e < E; ++e)
-						{
-							dst[r][e] = k0 + e < len ? __ldg(src + e) : T(0);
-						}
+						dst[r][e] = t[e];
 					}
 				}
-			};
-			T nxt[R][E];
-			if ((uint32_t) lane * E < padded)
-			{
-				fetch(nxt, (uint32_t) lane * E);
-			}
-			for (uint32_t k0 = (uint32_t) lane * E; k0 < padded; k0 += 32 * E)
-			{
-				T a[R][E];
-#pragma unroll
-				for (int r = 0; r < R; ++r)
+				else
 				{
 #pragma unroll
 					for (int e = 0; e < E; ++e)
 					{
-						a[r][e] = nxt[r][e];
-					}
-				}
-				if (k0 + 32 * E < padded)
-				{
-					fetch(nxt, k0 + 32 * E);
-				}
-#pragma unroll
-				for (int n = 0; n < SKINNY_MAX; ++n)
-				{
-					if (n < N)
-					{
-						V bv = *reinterpret_cast<const V*>(bs + n * PITCH + k0);
-						const T* bt = reinterpret_cast<const T*>(&bv);
-#pragma unroll
-						for (int e = 0; e < E; ++e)
-						{
-#pragma unroll
-							for (int r = 0; r < R; ++r)
-							{
-								acc[g][r][n] = fma_t(a[r][e], bt[e], acc[g][r][n]);
-							}
-						}
+						dst[r][e] = k0 + e < len ? __ldg(src + e) : T(0);
 					}
 				}
 			}
-		}
-	}
-#pragma unroll
-	for (int g = 0; g < GROUPS; ++g)
-	{
-		uint64_t row0 = cta_row0 + (uint64_t) (g * 8 + warp) * R;
-#pragma unroll
-		for (int r = 0; r < R; ++r)
+		};
+		auto multiply = [&] (const T (&a)[R][E], uint32_t k0)
 		{
 #pragma unroll
-			for (int n = 0; n < SKINNY_MAX; ++n)
+			for (int n = 0; n < NN; ++n)
 			{
-				if (n < N)
-				{
-					T v = acc[g][r][n];
+				V bv = *reinterpret_cast<const V*>(bs + n * pitch + k0);
+				const T* bt = reinterpret_cast<const T*>(&bv);
 #pragma unroll
-					for (int off = 16; off > 0; off >>= 1)
+				for (int e = 0; e < E; ++e)
+				{
+#pragma unroll
+					for (int r = 0; r < R; ++r)
 					{
-						v = v + __shfl_xor_sync(0xffffffffu, v, off);
-					}
-					if (0 == lane && row0 + r < p.M)
-					{
-						C[(int64_t) (row0 + r) * p.c_rs + (int64_t) n * p.c_cs] = v;
+						acc[r][n] = fma_t(a[r][e], bt[e], acc[r][n]);
 					}
 				}
 			}
+		};
+		// three rotating buffers: the loads of the next two steps are
+		// outstanding while a step is multiplied
+		constexpr uint32_t S = 32 * E;
+		uint32_t k0 = (uint32_t) lane * E;
+		T b0[R][E], b1[R][E], b2[R][E];
+		fetch(b0, k0);
+		fetch(b1, k0 + S);
+		for (; k0 < padded; k0 += 3 * S)
+		{
+			fetch(b2, k0 + 2 * S);
+			multiply(b0, k0);
+			if (k0 + S < padded)
+			{
+				fetch(b0, k0 + 3 * S);
+				multiply(b1, k0 + S);
+			}
+			if (k0 + 2 * S < padded)
+			{
+				fetch(b1, k0 + 4 * S);
+				multiply(b2, k0 + 2 * S);
+			}
 		}
 	}
+	if (false == live)
+	{
+		continue;
+	}
+#pragma unroll
+	for (int r = 0; r < R; ++r)
+	{
+#pragma unroll
+		for (int n = 0; n < NN; ++n)
+		{
+			T v = acc[r][n];
+#pragma unroll
+			for (int off = 16; off > 0; off >>= 1)
+			{
+				v = v + __shfl_xor_sync(0xffffffffu, v, off);
+			}
+			if (0 == lane && row0 + r < p.M && n < N)
+			{
+				C[(int64_t) (row0 + r) * p.c_rs + (int64_t) n * p.c_cs] = v;
+			}
+		}
+	}
+	} // row groups
 }
 
 // ---- skinny output, A contiguous along m (stored [k][m]), long k ---------------------
-// thread = one m (a warp reads 128 contiguous bytes of A per k), block y = one
-// k range whose rows of B sit in shared memory (every lane reads the same
-// word: a broadcast); partial sums part[y][m][n] are added in ascending y by
-// skinny_fold_kernel
+// thread = E consecutive m (a warp reads 512 contiguous bytes of A per k, one
+// 128-bit load per lane; UNROLL k's in flight = 128 bytes per lane), block y =
+// one k range whose rows of B sit in shared memory (every lane reads the same
+// words: broadcasts); partial sums part[y][m][n] are added in ascending y by
+// skinny_fold_kernel.  Per output the k's of a range are added in ascending
+// order.
 
 constexpr int SKINNY_COLS_THREADS = 128;
 
-template <typename T>
+template <typename T, int NN>
 __global__ void __launch_bounds__(SKINNY_COLS_THREADS)
 skinny_cols_kernel (T* __restrict__ part, const T* __restrict__ A,
-	const T* __restrict__ B, GemmParams p, uint32_t k_per_block)
+	const T* __restrict__ B, GemmParams p, uint32_t k_per_block, int a_vec)
 {
+	constexpr int E = 16 / (int) sizeof(T);
 	constexpr int SKINNY_KC = skinny_kc<T>();
-	__shared__ T bs[SKINNY_KC * SKINNY_MAX];
-	uint64_t m = (uint64_t) blockIdx.x * SKINNY_COLS_THREADS + threadIdx.x;
+	constexpr int UNROLL = 8;
+	using V = typename std::conditional<8 == sizeof(T), double2, float4>::type;
+	__shared__ __align__(16) T bs[SKINNY_KC * NN];
+	uint64_t m0 = ((uint64_t) blockIdx.x * SKINNY_COLS_THREADS + threadIdx.x) * E;
 	const int N = (int) p.N;
 	uint32_t k_begin = blockIdx.y * k_per_block;
 	uint32_t k_end = min((uint32_t) p.K, k_begin + k_per_block);
-	T acc[SKINNY_MAX];
+	T acc[E][NN];
 #pragma unroll
-	for (int n = 0; n < SKINNY_MAX; ++n)
+	for (int e = 0; e < E; ++e)
 	{
-		acc[n] = T(0);
+#pragma unroll
+		for (int n = 0; n < NN; ++n)
+		{
+			acc[e][n] = T(0);
+		}
 	}
-	const T* acol = A + (m < p.M ? m : p.M - 1); // a_rs == 1
+	const bool whole = a_vec && m0 + E <= p.M;   // one aligned 128-bit load per k
+	auto fetch = [&] (T (&dst)[E], uint32_t k)
+	{
+		const T* src = A + (int64_t) k * p.a_cs + m0; // a_rs == 1
+		if (whole)
+		{
+			V v = __ldcs(reinterpret_cast<const V*>(src));
+			const T* t = reinterpret_cast<const T*>(&v);
+#pragma unroll
+			for (int e = 0; e < E; ++e)
+			{
+				dst[e] = t[e];
+			}
+		}
+		else
+		{
+#pragma unroll
+			for (int e = 0; e < E; ++e)
+			{
+				dst[e] = m0 + e < p.M ? __ldg(src + e) : T(0);
+			}
+		}
+	};
 	for (uint32_t kc = k_begin; kc < k_end; kc += SKINNY_KC)
 	{
 		uint32_t len = min((uint32_t) SKINNY_KC, k_end - kc);
 		__syncthreads();
-		for (uint32_t i = threadIdx.x; i < len * SKINNY_MAX; i += SKINNY_COLS_THREADS)
+		for (uint32_t i = threadIdx.x; i < len * NN; i += SKINNY_COLS_THREADS)
 		{
-			uint32_t k = i / SKINNY_MAX;
-			uint32_t n = i % SKINNY_MAX;
+			uint32_t k = i / NN;
+			uint32_t n = i % NN;
 			bs[i] = (int) n < N ?
 				__ldg(B + (int64_t) (kc + k) * p.b_rs + (int64_t) n * p.b_cs) : T(0);
 		}
 		__syncthreads();
-#pragma unroll 8
-		for (uint32_t k = 0; k < len; ++k)
+		if (m0 >= p.M)
 		{
-			T a = __ldcs(acol + (int64_t) (kc + k) * p.a_cs);
-			const T* brow = bs + k * SKINNY_MAX;
+			continue;
+		}
+		uint32_t k = 0;
+		for (; k + UNROLL <= len; k += UNROLL)
+		{
+			T a[UNROLL][E];
 #pragma unroll
-			for (int n = 0; n < SKINNY_MAX; ++n)
+			for (int u = 0; u < UNROLL; ++u)
 			{
-				if (n < N)
+				fetch(a[u], kc + k + u);
+			}
+#pragma unroll
+			for (int u = 0; u < UNROLL; ++u)
+			{
+				const T* brow = bs + (k + u) * NN;
+#pragma unroll
+				for (int n = 0; n < NN; ++n)
 				{
-					acc[n] = fma_t(a, brow[n], acc[n]);
+					T bv = brow[n];
+#pragma unroll
+					for (int e = 0; e < E; ++e)
+					{
+						acc[e][n] = fma_t(a[u][e], bv, acc[e][n]);
+					}
+				}
+			}
+		}
+		for (; k < len; ++k)
+		{
+			T a[E];
+			fetch(a, kc + k);
+			const T* brow = bs + k * NN;
+#pragma unroll
+			for (int n = 0; n < NN; ++n)
+			{
+#pragma unroll
+				for (int e = 0; e < E; ++e)
+				{
+					acc[e][n] = fma_t(a[e], brow[n], acc[e][n]);
 				}
 			}
 		}
 	}
-	if (m < p.M)
-	{
-		T* dst = part + ((size_t) blockIdx.y * p.M + m) * SKINNY_MAX;
 #pragma unroll
-		for (int n = 0; n < SKINNY_MAX; ++n)
+	for (int e = 0; e < E; ++e)
+	{
+		if (m0 + e < p.M)
 		{
-			dst[n] = acc[n];
+			T* dst = part + ((size_t) blockIdx.y * p.M + m0 + e) * SKINNY_MAX;
+#pragma unroll
+			for (int n = 0; n < NN; ++n)
+			{
+				dst[n] = acc[e][n];
+			}
 		}
 	}
 }
@@ -319,25 +412,37 @@ int skinny_launch (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A0,
 	{
 		transpose_problem(p, A, B); // the short dimension becomes N
 	}
+	int nn = (int) ((p.N + 3) / 4 * 4);
 	if (1 == p.a_cs)
 	{
-		// A rows run along k
-		// rows per CTA = 8 warps x R x GROUPS; more groups amortise the staging
-		// of B but need enough rows to fill the machine
-		constexpr int R = 2;
+		// A rows run along k: 8 warps x R rows per CTA; B staged whole when
+		// it fits 48 KB (two CTAs per SM), else in chunks
 		constexpr int E = 16 / (int) sizeof(T);
 		int a_vec = (0 == ((uintptr_t) A & 15u) && 0 == p.a_rs % E) ? 1 : 0;
-		uint64_t per1 = 8 * R;
-		constexpr int G = 4 == sizeof(T) ? 2 : 1; // (fp64 accumulators of 2 groups would spill)
-		if (G > 1 && p.M >= per1 * G * (uint64_t) ctx->sm_count * 2)
+		uint32_t kpad = (uint32_t) ((p.K + E - 1) / E * E);
+		// (up to 96 KB: two CTAs per SM still fit)
+		uint32_t kfit = (uint32_t) (96 * 1024 / (nn * sizeof(T)) - E) / (32 * E) * (32 * E);
+		uint32_t kcap = std::min(kpad, std::max<uint32_t>(kfit, 32 * E));
+		size_t smem = (size_t) nn * (kcap + E) * sizeof(T);
+		switch (nn)
 		{
-			skinny_rows_kernel<T,R,G><<<(unsigned) ((p.M + per1 * G - 1) / (per1 * G)), 256, 0,
-				ctx->stream>>>(C, (const T*) A, (const T*) B, p, a_vec);
-		}
-		else
-		{
-			skinny_rows_kernel<T,R,1><<<(unsigned) ((p.M + per1 - 1) / per1), 256, 0,
-				ctx->stream>>>(C, (const T*) A, (const T*) B, p, a_vec);
+#define LLO_ROWS(NN) case NN:\
+			{\
+				constexpr int R = skinny_rows_r<T,NN>();\
+				unsigned blocks = (unsigned) ((p.M + 8 * R - 1) / (8 * R));\
+				if (kcap >= kpad)\
+				{\
+					blocks = std::min(blocks, (unsigned) ctx->sm_count * 2);\
+				}\
+				LLO_CUDA_TRY(cudaFuncSetAttribute(skinny_rows_kernel<T,NN>,\
+					cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));\
+				skinny_rows_kernel<T,NN><<<blocks, 256, smem, ctx->stream>>>(\
+					C, (const T*) A, (const T*) B, p, a_vec, kcap);\
+			}\
+			break;
+			LLO_ROWS(4) LLO_ROWS(8) LLO_ROWS(12) LLO_ROWS(16)
+#undef LLO_ROWS
+			default: return LLO_OK;
 		}
 		handled = true;
 		return launched(ctx, "skinny_rows_kernel");
@@ -345,9 +450,12 @@ int skinny_launch (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A0,
 	if (1 == p.a_rs)
 	{
 		// A stored [k][m]: split k over enough blocks to fill the machine
-		uint32_t mblocks = (uint32_t) ((p.M + SKINNY_COLS_THREADS - 1) / SKINNY_COLS_THREADS);
+		constexpr int E = 16 / (int) sizeof(T);
+		int a_vec = (0 == ((uintptr_t) A & 15u) && 0 == p.a_cs % E) ? 1 : 0;
+		uint64_t per_block = (uint64_t) SKINNY_COLS_THREADS * E;
+		uint32_t mblocks = (uint32_t) ((p.M + per_block - 1) / per_block);
 		uint32_t want = (uint32_t) std::max<uint64_t>(1,
-			((uint64_t) ctx->sm_count * 4 + mblocks - 1) / mblocks);
+			((uint64_t) ctx->sm_count * 6 + mblocks - 1) / mblocks);
 		uint32_t k_per_block = (uint32_t) std::max<uint64_t>(64, (p.K + want - 1) / want);
 		uint32_t splits = (uint32_t) ((p.K + k_per_block - 1) / k_per_block);
 		if (splits > 65535)
@@ -357,8 +465,15 @@ int skinny_launch (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A0,
 		Scratch scratch(ctx);
 		void* ws = nullptr;
 		LLO_TRY(scratch.get(&ws, (size_t) splits * p.M * SKINNY_MAX * sizeof(T)));
-		skinny_cols_kernel<T><<<dim3(mblocks, splits), SKINNY_COLS_THREADS, 0, ctx->stream>>>(
-			(T*) ws, (const T*) A, (const T*) B, p, k_per_block);
+		dim3 grid(mblocks, splits);
+		switch (nn)
+		{
+#define LLO_COLS(NN) case NN: skinny_cols_kernel<T,NN><<<grid, SKINNY_COLS_THREADS, 0, ctx->stream>>>(\
+			(T*) ws, (const T*) A, (const T*) B, p, k_per_block, a_vec); break;
+			LLO_COLS(4) LLO_COLS(8) LLO_COLS(12) LLO_COLS(16)
+#undef LLO_COLS
+			default: return LLO_OK;
+		}
 		LLO_TRY(launched(ctx, "skinny_cols_kernel"));
 		uint64_t total = p.M * SKINNY_MAX;
 		skinny_fold_kernel<T><<<(unsigned) ((total + 255) / 256), 256, 0,

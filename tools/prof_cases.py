@@ -78,6 +78,35 @@ def main():
 
         def run():
             capi.check(lib.llo_cuda_nnary(ctx.handle, capi.OPCODES["SUM"], F4, small, oshape, C.byref(arg), 1))
+    elif args.case == "convert":
+        # GenericData::copyover: f32 -> f64 of 2^26 elements
+        n26 = min(n, 1 << 26)
+        wide = ctx.alloc(n26 * 8)
+
+        def run():
+            capi.check(lib.llo_cuda_convert(ctx.handle, wide, capi.dtype_code(np.float64), x, F4, n26))
+    elif args.case == "rand":
+        # rand_unif over 2^26 fp32 outputs, scalar bounds broadcast by an extend map
+        n26 = min(n, 1 << 26)
+        ext = np.zeros((9, 9))
+        ext[8][8] = 1.0
+        lo_h, hi_h = ctx.upload(np.array([2.0], dtype=np.float32)), ctx.upload(np.array([9.0], dtype=np.float32))
+        a_lo, a_hi = capi.make_arg(lo_h, [], ext, False), capi.make_arg(hi_h, [], ext, False)
+        oshape = capi.shape8([8192, n26 // 8192])
+
+        def run():
+            capi.check(lib.llo_cuda_rand(ctx.handle, capi.OPCODES["RAND_UNIF"], F4, out, oshape, C.byref(a_lo), C.byref(a_hi)))
+    elif args.case == "general":
+        # a fractional coordinate map (nearest-neighbour upsample by 3 along dim 1): the
+        # per-element double-precision path of general.cu, 2^24 outputs
+        m = np.eye(9)
+        m[1][1] = 1.0 / 3
+        rows = 1 << 10
+        arg = capi.make_arg(x, [4096, rows], m, False)
+        oshape = capi.shape8([4096, rows * 3])
+
+        def run():
+            capi.check(lib.llo_cuda_nnary(ctx.handle, capi.OPCODES["SUM"], F4, out, oshape, C.byref(arg), 1))
     else:
         raise SystemExit("unknown case " + args.case)
     start, stop = ctx.event(), ctx.event()
