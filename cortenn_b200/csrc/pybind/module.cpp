@@ -32,6 +32,9 @@
 
 #include "dbg/ade.hpp"
 
+#include "llo/serialize.hpp"
+#include "pbm/pbm.hpp"
+
 namespace py = pybind11;
 
 namespace pyllo
@@ -605,6 +608,108 @@ PYBIND11_MODULE(_C, m)
 			peq.print(ss, root);
 			return ss.str();
 		}, py::arg("root"), py::arg("showshape") = false);
+
+	// ---- pbm: marshal / unmarshal graphs (pbm/save.hpp, pbm/load.hpp) ----
+	llo_m.def("save_graph", [](std::vector<T> roots,
+		std::vector<std::pair<T,std::vector<std::string>>> labels, std::string graph_label)
+		{
+			pbm::GraphSaver saver(llo::serialize);
+			for (T& root : roots)
+			{
+				root->accept(saver);
+			}
+			pbm::PathedMapT paths;
+			for (auto& entry : labels)
+			{
+				paths[entry.first] = pbm::StringsT(entry.second.begin(), entry.second.end());
+			}
+			pbm::Graph graph;
+			graph.label_ = graph_label;
+			saver.save(graph, paths);
+			return py::bytes(pbm::encode(graph));
+		}, "marshal the graphs under `roots` to the bytes of a cortenn.Graph message "
+		"(pbm/graph.proto); `labels` = [(tensor, [path, ...]), ...]",
+		py::arg("roots"), py::arg("labels") = std::vector<std::pair<T,std::vector<std::string>>>(),
+		py::arg("label") = "");
+	llo_m.def("load_graph", [](py::bytes data)
+		{
+			pbm::Graph graph;
+			pbm::decode(graph, std::string(data));
+			pbm::GraphInfo info;
+			pbm::load_graph(info, graph, llo::deserialize);
+			py::dict out;
+			out["label"] = graph.label_;
+			out["nodes"] = info.nodes_;
+			std::vector<T> roots;
+			for (const T& node : info.nodes_)
+			{
+				if (info.roots_.end() != info.roots_.find(node))
+				{
+					roots.push_back(node);
+				}
+			}
+			out["roots"] = roots;
+			py::list labelled;
+			for (size_t i = 0; i < graph.nodes_.size(); ++i)
+			{
+				if (false == graph.nodes_[i].labels_.empty())
+				{
+					labelled.append(py::make_tuple(graph.nodes_[i].labels_, info.nodes_[i]));
+				}
+			}
+			out["labelled"] = labelled;
+			return out;
+		}, "unmarshal a cortenn.Graph message: {label, nodes (file order), roots, "
+		"labelled: [(path, tensor)]}; leaves become llo Variables");
+	llo_m.def("pbm_decode", [](py::bytes data)
+		{
+			pbm::Graph graph;
+			pbm::decode(graph, std::string(data));
+			py::list nodes;
+			for (const pbm::Node& node : graph.nodes_)
+			{
+				py::dict n;
+				n["labels"] = node.labels_;
+				if (node.has_source_)
+				{
+					py::dict src;
+					src["shape"] = py::bytes(node.source_.shape_);
+					src["wide_shape"] = node.source_.wide_shape_;
+					src["data"] = py::bytes(node.source_.data_);
+					src["typecode"] = node.source_.typecode_;
+					n["source"] = src;
+				}
+				if (node.has_functor_)
+				{
+					py::dict fn;
+					fn["opname"] = node.functor_.opname_;
+					fn["opcode"] = node.functor_.opcode_;
+					py::list args;
+					for (const pbm::NodeArg& arg : node.functor_.args_)
+					{
+						py::dict a;
+						a["idx"] = arg.idx_;
+						a["coord"] = arg.coord_;
+						a["shaper"] = arg.shaper_;
+						a["fwd"] = arg.fwd_;
+						args.append(a);
+					}
+					fn["args"] = args;
+					n["functor"] = fn;
+				}
+				nodes.append(n);
+			}
+			py::dict out;
+			out["label"] = graph.label_;
+			out["nodes"] = nodes;
+			return out;
+		}, "the messages of a cortenn.Graph file as dictionaries (no tensors are built)");
+	llo_m.def("pbm_reencode", [](py::bytes data)
+		{
+			pbm::Graph graph;
+			pbm::decode(graph, std::string(data));
+			return py::bytes(pbm::encode(graph));
+		}, "decode and encode again (byte-identical for files of the reference's writer)");
 
 	// ---- device-resident additions ----
 	py::class_<pyllo::DeviceResult>(llo_m, "DeviceResult")
