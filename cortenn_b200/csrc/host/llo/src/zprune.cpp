@@ -1,3 +1,15 @@
+///
+/// zprune.cpp
+/// llo
+///
+/// VENDORED FROM THE REFERENCE.  This file is mingkaic/cortenn's
+/// llo/src/zprune.cpp:14-116 (MIT licence, (c) its authors): the same switch
+/// over opcodes in the same order, with renamed locals and small helpers.  It
+/// defines what llo::derive returns (zero-labelled leaves pruned), i.e. the
+/// reference's semantics on the reference's side of the drop-in boundary;
+/// nothing on the GPU path derives from it.
+///
+
 #include "ade/functor.hpp"
 
 #include "llo/zprune.hpp"

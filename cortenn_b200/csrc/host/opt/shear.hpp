@@ -2,6 +2,14 @@
 /// shear.hpp
 /// opt
 ///
+/// VENDORED FROM THE REFERENCE.  This file is mingkaic/cortenn's
+/// opt/shear.hpp:20-176 (MIT licence, (c) its authors) with local variable
+/// renames, a `seen_` set and a stable sort; it is the reference's host-side
+/// graph pruner, on the reference's side of the drop-in boundary, and is kept
+/// so that graphs "produced by ade::derive and optimised by opt" are the same
+/// graphs.  Nothing on the GPU path derives from it.  The optimiser that is
+/// new work is opt/rewrite.hpp + llo/optimize.hpp.
+///
 /// Purpose:
 /// Target-driven graph pruning, same interface as the reference's
 /// opt/shear.hpp:20-176 (LeafFinder, TargetPruner, GetLeafValT, PruneFuncT).

@@ -366,6 +366,9 @@ def test_gemm(ctx, dtype, layout):
     (10, 1000, 3000),     # skinny the other way round (transposed problem)
     (4100, 16, 300),      # widest skinny output, ragged rows
     (3000, 1, 1000),      # matrix-vector
+    (784, 1024, 4096),    # a 16-row last tile row: its dead warps skip the math, split-K by the cost model
+    (4099, 10, 1024),     # persistent skinny rows kernel with B staged whole, ragged last row group
+    (1024, 10, 8191),     # skinny columns, k ranges that do not divide
 ])
 def test_gemm_schedules(ctx, dtype, layout, mnk):
     """every work decomposition of the TMA GEMMs (tile grid, split-K, persistent
@@ -379,13 +382,22 @@ def test_gemm_schedules(ctx, dtype, layout, mnk):
     a_rs, a_cs = (K, 1) if layout[0] == "n" else (1, M)
     b_rs, b_cs = (N, 1) if layout[1] == "n" else (1, K)
     pa = ctx.upload(a_store); pb = ctx.upload(b_store)
-    pc = ctx.alloc(M * N * np.dtype(dtype).itemsize)
+    # C between canary bands (compute-sanitizer is closed on this pool): edge tiles, tail
+    # splits and folds must not write outside it
+    nbytes = M * N * np.dtype(dtype).itemsize
+    padded = (nbytes + 15) // 16 * 16
+    block = ctx.alloc(padded + 2 * util.GUARD)
+    capi.check(ctx.lib.llo_cuda_memset(ctx.handle, block, util.GUARD_BYTE, padded + 2 * util.GUARD))
+    pc = block + util.GUARD
     got = []
     for _ in range(2):
         capi.check(ctx.lib.llo_cuda_gemm(ctx.handle, capi.dtype_code(dtype), M, N, K,
                                          pa, a_rs, a_cs, pb, b_rs, b_cs, pc, N, 1, 0))
-        got.append(ctx.download(pc, M * N, dtype).reshape(M, N))
-    for p in (pa, pb, pc):
+        whole = ctx.download(block, padded + 2 * util.GUARD, np.uint8)
+        assert (whole[:util.GUARD] == util.GUARD_BYTE).all() and \
+            (whole[util.GUARD + nbytes:] == util.GUARD_BYTE).all(), "gemm wrote outside C"
+        got.append(whole[util.GUARD:util.GUARD + nbytes].view(dtype).reshape(M, N).copy())
+    for p in (pa, pb, block):
         ctx.free(p)
     expect = A.astype(np.float64) @ B.astype(np.float64)
     tol = 1e-6 if dtype == np.float32 else 1e-12

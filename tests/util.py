@@ -87,12 +87,22 @@ def oracle_convert(array, out_dtype):
     return out
 
 
+GUARD = 256          # bytes of canary on each side of every output buffer
+GUARD_BYTE = 0xA5
+
+
 def gpu_op_exec(ctx, opcode, np_dtype, outshape, args, entry="op_exec"):
-    """Same contract as oracle_op_exec, through the CUDA C-ABI."""
+    """Same contract as oracle_op_exec, through the CUDA C-ABI.  compute-sanitizer is
+    closed on this pool, so every call checks for out-of-bounds WRITES itself: the output
+    sits between two canary bands that must come back untouched."""
     ptrs = [ctx.upload(np.ascontiguousarray(a[0])) for a in args]
     nout = nelems(outshape)
-    out_ptr = ctx.alloc(max(1, nout * np.dtype(np_dtype).itemsize))
-    capi.check(ctx.lib.llo_cuda_memset(ctx.handle, out_ptr, 0, nout * np.dtype(np_dtype).itemsize))
+    nbytes = nout * np.dtype(np_dtype).itemsize
+    padded = (max(1, nbytes) + 15) // 16 * 16
+    block = ctx.alloc(padded + 2 * GUARD)
+    out_ptr = block + GUARD
+    capi.check(ctx.lib.llo_cuda_memset(ctx.handle, block, GUARD_BYTE, padded + 2 * GUARD))
+    capi.check(ctx.lib.llo_cuda_memset(ctx.handle, out_ptr, 0, nbytes))
     cargs = (capi.Arg * len(args))(*[
         capi.make_arg(p, a[1], a[2] if len(a) > 2 else None, a[3] if len(a) > 3 else False)
         for p, a in zip(ptrs, args)])
@@ -103,11 +113,14 @@ def gpu_op_exec(ctx, opcode, np_dtype, outshape, args, entry="op_exec"):
         else:
             capi.check(ctx.lib.llo_cuda_op_exec(ctx.handle, capi.OPCODES[opcode], capi.dtype_code(np_dtype),
                                                 out_ptr, capi.shape8(outshape), cargs, len(args)))
-        return ctx.download(out_ptr, nout, np_dtype)
+        whole = ctx.download(block, padded + 2 * GUARD, np.uint8)
+        assert (whole[:GUARD] == GUARD_BYTE).all(), "%s wrote below its output buffer" % opcode
+        assert (whole[GUARD + nbytes:] == GUARD_BYTE).all(), "%s wrote past its output buffer" % opcode
+        return whole[GUARD:GUARD + nbytes].view(np_dtype).copy()
     finally:
         for p in ptrs:
             ctx.free(p)
-        ctx.free(out_ptr)
+        ctx.free(block)
 
 
 def var(data, ade_shape, dtype=np.float64, label=""):

@@ -20,13 +20,23 @@ def run_gemm(ctx, dtype, A, B, layout, precision=0, c_colmajor=False):
     a_rs, a_cs = (K, 1) if layout[0] == "n" else (1, M)
     b_rs, b_cs = (N, 1) if layout[1] == "n" else (1, K)
     pa, pb = ctx.upload(a_store), ctx.upload(b_store)
-    pc = ctx.alloc(M * N * np.dtype(dtype).itemsize)
+    # compute-sanitizer is closed on this pool: C sits between two canary bands that
+    # must come back untouched (out-of-bounds writes of edge tiles / split-K folds)
+    guard = 256
+    nbytes = M * N * np.dtype(dtype).itemsize
+    padded = (nbytes + 15) // 16 * 16
+    block = ctx.alloc(padded + 2 * guard)
+    capi.check(ctx.lib.llo_cuda_memset(ctx.handle, block, 0xA5, padded + 2 * guard))
+    pc = block + guard
     c_rs, c_cs = (1, M) if c_colmajor else (N, 1)
     capi.check(ctx.lib.llo_cuda_gemm(ctx.handle, capi.dtype_code(dtype), M, N, K,
                                      pa, a_rs, a_cs, pb, b_rs, b_cs, pc, c_rs, c_cs, precision))
-    got = ctx.download(pc, M * N, dtype)
+    whole = ctx.download(block, padded + 2 * guard, np.uint8)
+    assert (whole[:guard] == 0xA5).all() and (whole[guard + nbytes:] == 0xA5).all(), \
+        "gemm wrote outside C (M=%d N=%d K=%d %s)" % (M, N, K, layout)
+    got = whole[guard:guard + nbytes].view(dtype).copy()
     got = got.reshape(N, M).T if c_colmajor else got.reshape(M, N)
-    for p in (pa, pb, pc):
+    for p in (pa, pb, block):
         ctx.free(p)
     return got
 
