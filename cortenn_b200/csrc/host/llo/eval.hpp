@@ -35,9 +35,17 @@ struct EvalMemo final
 		return done_[(size_t) dtype];
 	}
 
+	/// True when `tens` is or contains a RAND_* functor: such sub-graphs are
+	/// re-evaluated on every visit (fresh draws, llo/eval.hpp:77-87 of the
+	/// reference re-runs every child), exactly like the planner never shares
+	/// them -- the two modes then sample alike
+	bool has_random (ade::iTensor* tens);
+
 private:
 	std::unordered_map<ade::iTensor*,GenericData> done_[
 		age::_N_GENERATED_DTYPES];
+
+	std::unordered_map<ade::iTensor*,bool> random_;
 };
 
 /// Visitor implementation to evaluate ade nodes according to dtype

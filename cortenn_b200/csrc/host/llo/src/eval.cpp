@@ -13,6 +13,26 @@ static bool is_random (size_t opcode)
 		age::RAND_NORM == opcode;
 }
 
+bool EvalMemo::has_random (ade::iTensor* tens)
+{
+	auto it = random_.find(tens);
+	if (random_.end() != it)
+	{
+		return it->second;
+	}
+	bool out = false;
+	if (auto func = dynamic_cast<ade::iFunctor*>(tens))
+	{
+		out = is_random(func->get_opcode().code_);
+		for (const ade::MappedTensor& child : func->get_children())
+		{
+			out = has_random(child.get_tensor().get()) || out;
+		}
+	}
+	random_.emplace(tens, out);
+	return out;
+}
+
 void Evaluator::visit (ade::iLeaf* leaf)
 {
 	const ade::Shape& shape = leaf->shape();
@@ -36,7 +56,8 @@ void Evaluator::visit (ade::iFunctor* func)
 	size_t code = func->get_opcode().code_;
 	age::_GENERATED_OPCODE opcode = (age::_GENERATED_OPCODE) code;
 	auto& done = memo_->of(dtype_);
-	if (false == is_random(code))
+	const bool fresh = memo_->has_random(func);
+	if (false == fresh)
 	{
 		auto it = done.find(func);
 		if (done.end() != it)
@@ -72,7 +93,7 @@ void Evaluator::visit (ade::iFunctor* func)
 
 	out_ = GenericData(func->shape(), dtype_);
 	op_exec(opcode, out_.dtype_, out_.device_.get(), out_.shape_, argdata);
-	if (false == is_random(code))
+	if (false == fresh)
 	{
 		done.emplace(func, out_);
 	}

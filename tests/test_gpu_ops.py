@@ -25,7 +25,15 @@ def tolerance(dtype):
     return 0
 
 
-def assert_parity(expect, got, dtype, what=""):
+# operators whose result can pass through zero with a finite slope keep an absolute floor
+# at unit scale (the north star's 1e-6 / 1e-12 is relative; sin / cos / tan / log of a value
+# next to one of their zeros has an unbounded RELATIVE condition number, so two correctly
+# rounded libm's differ by more than that there); everything else is held to true relative
+# error (IEEE + - * / sqrt are bit-identical, exp / pow within their libm ulps)
+ABSOLUTE_FLOOR_OPS = ("SIN", "COS", "TAN", "LOG")
+
+
+def assert_parity(expect, got, dtype, what="", floor=True):
     tol = tolerance(dtype)
     if tol == 0:
         np.testing.assert_array_equal(expect, got, err_msg=what)
@@ -38,8 +46,9 @@ def assert_parity(expect, got, dtype, what=""):
     # relative to the reference value, with an absolute floor of the same
     # factor at unit scale (sin / cos / log near their zeros)
     err = np.abs(expect[fin] - got[fin])
-    bound = tol * np.maximum(np.abs(expect[fin]), 1.0)
-    assert (err <= bound).all(), "%s: max err %g" % (what, (err / np.maximum(np.abs(expect[fin]), 1.0)).max())
+    scale = np.maximum(np.abs(expect[fin]), 1.0) if floor else np.abs(expect[fin])
+    bound = tol * scale
+    assert (err <= bound).all(), "%s: max err %g" % (what, (err / np.maximum(scale, 1e-300)).max())
 
 
 def sample(rng, dtype, n, lo=0.5, hi=3.0, positive=True):
@@ -84,7 +93,7 @@ def test_unary_identity(ctx, op, dtype):
         return
     expect = util.oracle_op_exec(op, dtype, shape, args)
     got = util.gpu_op_exec(ctx, op, dtype, shape, args)
-    assert_parity(expect, got, dtype, "%s %s" % (op, dtype.__name__))
+    assert_parity(expect, got, dtype, "%s %s" % (op, dtype.__name__), floor=op in ABSOLUTE_FLOOR_OPS)
 
 
 @pytest.mark.parametrize("dtype", ALL_DTYPES)
@@ -103,7 +112,7 @@ def test_binary_identity(ctx, op, dtype):
     args = [(a, shape), (b, shape)]
     expect = util.oracle_op_exec(op, dtype, shape, args)
     got = util.gpu_op_exec(ctx, op, dtype, shape, args)
-    assert_parity(expect, got, dtype, "%s %s" % (op, dtype.__name__))
+    assert_parity(expect, got, dtype, "%s %s" % (op, dtype.__name__), floor=False)
 
 
 @pytest.mark.parametrize("dtype", ALL_DTYPES)
@@ -118,7 +127,7 @@ def test_nnary_identity(ctx, op, dtype, nargs):
                    else rng.integers(1, 3, n).astype(dtype)), shape) for _ in range(nargs)]
     expect = util.oracle_op_exec(op, dtype, shape, args)
     got = util.gpu_op_exec(ctx, op, dtype, shape, args)
-    assert_parity(expect, got, dtype, "%s x%d %s" % (op, nargs, dtype.__name__))
+    assert_parity(expect, got, dtype, "%s x%d %s" % (op, nargs, dtype.__name__), floor=False)
 
 
 # ---- coordinate maps --------------------------------------------------------
