@@ -542,6 +542,34 @@ def side_workloads(args, timer, age, llo, rank, world):
                 entry["verified"] = bool(err <= (1e-6 if dt == np.float32 else 1e-12))
             out[name] = entry
             del va, vb, a, b, root, holder
+        # age.convolution lowered to im2col gather + one TMA GEMM
+        nb, side_i, ic, oc, kw = 32, 128, 32, 64, 3
+        img = np.random.default_rng(8).uniform(-1, 1, (nb, side_i, side_i, ic)).astype(np.float32)
+        ker = np.random.default_rng(9).uniform(-1, 1, (kw, kw, ic, oc)).astype(np.float32)
+        croot = age.convolution(llo.variable(img, "img"), llo.variable(ker, "k"))
+        holder = {}
+
+        def conv_step():
+            holder["res"] = llo.evaluate_device(croot, F32)
+        ms, launches = timer.timed(conv_step, steps, warm)
+        st = llo.plan_stats()
+        so = side_i - kw + 1
+        cflops = 2.0 * nb * so * so * ic * kw * kw * oc
+        entry = {"ms": round(ms, 4), "TFLOPs": round(cflops / ms / 1e9, 2), "launches": launches // steps,
+                 "shape": "img [%d,%d,%d,%d] x kernel [%d,%d,%d,%d], VALID" % (nb, side_i, side_i, ic, kw, kw, ic, oc),
+                 "plan": {k: st[k] for k in ("gemms", "gathers", "generic", "programs")}}
+        if check:
+            got = holder["res"].numpy(F32)[:2].astype(np.float64)
+            want = np.zeros_like(got)
+            for a in range(kw):
+                for b in range(kw):
+                    want += np.einsum("nwhc,co->nwho", img[:2, a:a + so, b:b + so, :].astype(np.float64),
+                                      ker[a, b].astype(np.float64))
+            err = float(np.abs(got - want).max() / np.abs(want).max())
+            entry["max_err_over_max_abs"] = err
+            entry["verified"] = bool(err <= 1e-5)
+        out["convolution_f32"] = entry
+        del img, ker, croot, holder
     if not args.skip_mlp:
         out.update(mlp_workload(args, timer, age, llo, rank, world, steps, warm, check))
     return out

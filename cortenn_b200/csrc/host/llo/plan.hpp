@@ -46,6 +46,7 @@ struct PlanStats
 	size_t programs_ = 0;     // elementwise program launches
 	size_t reduces_ = 0;      // reduction launches
 	size_t gemms_ = 0;        // contractions lowered to GEMM
+	size_t gathers_ = 0;      // GEMM operands gathered into a dense matrix first (im2col)
 	size_t generic_ = 0;      // functors run through age::op_exec
 	size_t simplified_ = 0;   // algebraic rewrites applied
 	size_t shared_ = 0;       // plan nodes merged with a structurally equal one
@@ -68,6 +69,12 @@ std::vector<GenericData> planned_eval_many (const ade::TensT& roots,
 
 /// Statistics of the most recent planned_eval on this thread
 const PlanStats& last_plan_stats (void);
+
+/// What the planner makes of the graphs WITHOUT evaluating them (no device
+/// needed): nodes, views, constants, sharing and how many functors fall back
+/// to the generic per-functor path.  Launch counts (programs / reduces /
+/// gemms) are only known after an evaluation.
+PlanStats plan_preview (const ade::TensT& roots, age::_GENERATED_DTYPE dtype);
 
 }
 

@@ -26,16 +26,48 @@ constexpr int R = ade::rank_cap;
 
 // ---- coordinate views -------------------------------------------------------
 
-/// target coordinate j = scale * c[src] + offset (src < 0: just offset)
+/// target coordinate j = sum_i coef[i] * c[i] + offset: one column of an
+/// integer affine coordinate map.  Most columns have a single source (extend,
+/// permute, flip); a convolution's image argument has two (h = oh + kh,
+/// llo/src/helper.cpp:149-165).
 struct DimMap
 {
-	int src_ = -1;
-	int64_t scale_ = 0;
+	int64_t coef_[R] = {0, 0, 0, 0, 0, 0, 0, 0};
 	int64_t offset_ = 0;
 
 	bool operator == (const DimMap& o) const
 	{
-		return src_ == o.src_ && scale_ == o.scale_ && offset_ == o.offset_;
+		return offset_ == o.offset_ &&
+			0 == std::memcmp(coef_, o.coef_, sizeof(coef_));
+	}
+
+	/// number of source coordinates the column depends on
+	int nsrc (void) const
+	{
+		int n = 0;
+		for (int i = 0; i < R; ++i)
+		{
+			n += 0 != coef_[i] ? 1 : 0;
+		}
+		return n;
+	}
+
+	/// the only source of a single-source column (-1: none or several)
+	int src (void) const
+	{
+		int found = -1;
+		for (int i = 0; i < R; ++i)
+		{
+			if (0 != coef_[i])
+			{
+				if (found >= 0)
+				{
+					return -1;
+				}
+				found = i;
+			}
+		}
+		return found;
 	}
 };
 
@@ -50,8 +82,7 @@ struct CoordView
 		CoordView v;
 		for (int j = 0; j < R; ++j)
 		{
-			v.t_[j].src_ = j;
-			v.t_[j].scale_ = 1;
+			v.t_[j].coef_[j] = 1;
 		}
 		return v;
 	}
@@ -76,18 +107,20 @@ static CoordView compose (const CoordView& outer, const CoordView& inner)
 	for (int k = 0; k < R; ++k)
 	{
 		const DimMap& in = inner.t_[k];
-		if (in.src_ < 0)
+		DimMap& o = out.t_[k];
+		o.offset_ = in.offset_;
+		for (int m = 0; m < R; ++m)
 		{
-			out.t_[k] = in;
-			continue;
-		}
-		const DimMap& mid = outer.t_[in.src_];
-		out.t_[k].src_ = (0 == in.scale_ * mid.scale_) ? -1 : mid.src_;
-		out.t_[k].scale_ = mid.src_ < 0 ? 0 : in.scale_ * mid.scale_;
-		out.t_[k].offset_ = in.scale_ * mid.offset_ + in.offset_;
-		if (out.t_[k].src_ < 0)
-		{
-			out.t_[k].scale_ = 0;
+			if (0 == in.coef_[m])
+			{
+				continue;
+			}
+			const DimMap& mid = outer.t_[m];
+			o.offset_ += in.coef_[m] * mid.offset_;
+			for (int i = 0; i < R; ++i)
+			{
+				o.coef_[i] += in.coef_[m] * mid.coef_[i];
+			}
 		}
 	}
 	return out;
@@ -105,10 +138,12 @@ static void normalise (CoordView& v, const ade::Shape& from, const ade::Shape& t
 			d = DimMap();
 			continue;
 		}
-		if (d.src_ >= 0 && (from.at(d.src_) <= 1 || 0 == d.scale_))
+		for (int i = 0; i < R; ++i)
 		{
-			d.src_ = -1;
-			d.scale_ = 0;
+			if (from.at(i) <= 1)
+			{
+				d.coef_[i] = 0;
+			}
 		}
 	}
 }
@@ -133,8 +168,9 @@ static bool is_integral (double v)
 }
 
 /// Column-wise analysis of matrix m taking box `from` to tensor `to`.
-/// Returns false when some target coordinate is not a single-source integer
-/// affine function.  Throws when a coordinate provably leaves `to`.
+/// Returns false when some target coordinate is not an integer affine
+/// function of the source coordinates.  Throws when a coordinate provably
+/// leaves `to`.
 static bool affine_columns (DimMap (&cols)[R], const ade::CoordptrT& mapper,
 	const ade::Shape& from, const ade::Shape& to)
 {
@@ -145,8 +181,6 @@ static bool affine_columns (DimMap (&cols)[R], const ade::CoordptrT& mapper,
 		{
 			double lo = m[R][j];
 			double hi = lo;
-			int nsrc = 0;
-			int src = -1;
 			bool integral = is_integral(lo);
 			for (int i = 0; i < R; ++i)
 			{
@@ -154,8 +188,6 @@ static bool affine_columns (DimMap (&cols)[R], const ade::CoordptrT& mapper,
 				{
 					continue;
 				}
-				++nsrc;
-				src = i;
 				integral = integral && is_integral(m[i][j]);
 				double span = m[i][j] * (double) (from.at(i) - 1);
 				(span < 0 ? lo : hi) += span;
@@ -172,7 +204,7 @@ static bool affine_columns (DimMap (&cols)[R], const ade::CoordptrT& mapper,
 			{
 				continue; // always wraps / truncates to 0
 			}
-			if (false == integral || nsrc > 1)
+			if (false == integral)
 			{
 				ok = false;
 				continue;
@@ -188,10 +220,12 @@ static bool affine_columns (DimMap (&cols)[R], const ade::CoordptrT& mapper,
 				shift = (int64_t) to.at(j);
 			}
 			cols[j].offset_ = (int64_t) m[R][j] + shift;
-			if (nsrc == 1)
+			for (int i = 0; i < R; ++i)
 			{
-				cols[j].src_ = src;
-				cols[j].scale_ = (int64_t) m[src][j];
+				if (from.at(i) > 1 && 0 != m[i][j])
+				{
+					cols[j].coef_[i] = (int64_t) m[i][j];
+				}
 			}
 		}
 	});
@@ -243,22 +277,23 @@ static MapInfo classify (const ade::MappedTensor& arg, const ade::Shape& outshap
 			continue;
 		}
 		const DimMap& c = cols[j];
-		if (c.src_ < 0 || (1 != c.scale_ && -1 != c.scale_) ||
-			fed[c.src_] || argshape.at(c.src_) != outshape.at(j))
+		int csrc = c.src();
+		int64_t cscale = csrc >= 0 ? c.coef_[csrc] : 0;
+		if (csrc < 0 || (1 != cscale && -1 != cscale) ||
+			fed[csrc] || argshape.at(csrc) != outshape.at(j))
 		{
 			return info;
 		}
 		// o = s * a + b  ->  a = s * o - s * b; must cover [0, n)
 		int64_t n = (int64_t) outshape.at(j);
-		if ((1 == c.scale_ && 0 != c.offset_) ||
-			(-1 == c.scale_ && n - 1 != c.offset_))
+		if ((1 == cscale && 0 != c.offset_) ||
+			(-1 == cscale && n - 1 != c.offset_))
 		{
 			return info;
 		}
-		fed[c.src_] = true;
-		inv.t_[c.src_].src_ = j;
-		inv.t_[c.src_].scale_ = c.scale_;
-		inv.t_[c.src_].offset_ = -c.scale_ * c.offset_;
+		fed[csrc] = true;
+		inv.t_[csrc].coef_[j] = cscale;
+		inv.t_[csrc].offset_ = -cscale * c.offset_;
 	}
 	for (int i = 0; i < R; ++i)
 	{
@@ -386,8 +421,7 @@ struct Plan
 	{
 		for (int j = 0; j < R; ++j)
 		{
-			put(key, v.t_[j].src_);
-			put(key, v.t_[j].scale_);
+			put(key, v.t_[j].coef_);
 			put(key, v.t_[j].offset_);
 		}
 	}
@@ -940,9 +974,9 @@ struct Plan
 		{
 			const DimMap& m = view.t_[j];
 			out.offset += m.offset_ * dense;
-			if (m.src_ >= 0)
+			for (int i = 0; i < R; ++i)
 			{
-				out.stride[m.src_] += m.scale_ * dense;
+				out.stride[i] += m.coef_[i] * dense;
 			}
 			dense *= (int64_t) nodeshape.at(j);
 		}
@@ -1281,9 +1315,9 @@ struct Plan
 			for (int i = 0; i < R; ++i)
 			{
 				const DimMap& m = n->kept_.t_[i];
-				if (m.src_ == j && n->shape_.at(j) > 1)
+				if (m.src() == j && n->shape_.at(j) > 1)
 				{
-					if (1 != m.scale_ || 0 != m.offset_)
+					if (1 != m.coef_[j] || 0 != m.offset_)
 					{
 						return false;
 					}
@@ -1292,31 +1326,14 @@ struct Plan
 			}
 			dense *= (int64_t) n->shape_.at(j);
 		}
-		struct Group
+		// dims of the argument space by role: M (A only), N (B only), K (folded,
+		// both); sizes and the strides each tensor has along them
+		struct Role
 		{
+			std::vector<int> dims_;
 			uint64_t size_ = 1;
-			int64_t s1_ = 0;
-			int64_t s2_ = 0;
-			bool any_ = false;
 		};
-		Group gm, gn, gk;
-		auto add_dim = [](Group& g, uint64_t size, int64_t s1, int64_t s2) -> bool
-		{
-			if (false == g.any_)
-			{
-				g.size_ = size;
-				g.s1_ = s1;
-				g.s2_ = s2;
-				g.any_ = true;
-				return true;
-			}
-			if (s1 != g.s1_ * (int64_t) g.size_ || s2 != g.s2_ * (int64_t) g.size_)
-			{
-				return false;
-			}
-			g.size_ *= size;
-			return true;
-		};
+		Role rm, rn, rk;
 		for (int i = 0; i < R; ++i)
 		{
 			uint64_t size = n->argshape_.at(i);
@@ -1326,41 +1343,120 @@ struct Plan
 			}
 			int64_t a = sa.stride[i];
 			int64_t b = sb.stride[i];
-			bool ok = false;
+			Role* role = nullptr;
 			if (folded[i])
 			{
-				ok = 0 != a && 0 != b && add_dim(gk, size, a, b);
+				role = (0 != a && 0 != b) ? &rk : nullptr;
 			}
 			else if (0 != a && 0 == b)
 			{
-				ok = add_dim(gm, size, a, sc[i]);
+				role = &rm;
 			}
 			else if (0 == a && 0 != b)
 			{
-				ok = add_dim(gn, size, b, sc[i]);
+				role = &rn;
 			}
-			if (false == ok)
+			if (nullptr == role)
 			{
 				return false;
 			}
+			role->dims_.push_back(i);
+			role->size_ *= size;
 		}
-		if (false == gk.any_)
+		if (rk.dims_.empty())
 		{
 			return false;
+		}
+		// a role's dims merge into ONE stride of a tensor when each dim's
+		// stride is the previous one's times its size
+		auto merged = [&](const Role& role, const int64_t* stride, int64_t& out) -> bool
+		{
+			out = 0;
+			uint64_t run = 1;
+			for (size_t q = 0; q < role.dims_.size(); ++q)
+			{
+				int i = role.dims_[q];
+				if (0 == q)
+				{
+					out = stride[i];
+				}
+				else if (stride[i] != out * (int64_t) run)
+				{
+					return false;
+				}
+				run *= n->argshape_.at(i);
+			}
+			return true;
+		};
+		int64_t c_m = 0, c_n = 0;
+		if (false == merged(rm, sc, c_m) || false == merged(rn, sc, c_n))
+		{
+			return false; // the output itself is not a matrix of the two roles
 		}
 		evaluate(fa.node_);
 		evaluate(fb.node_);
 		size_t esize = age::type_size(n->dtype_);
+		// An operand whose dims do not merge -- the image of a convolution: the
+		// window offsets kh, kw move along the same axes as oh, ow
+		// (llo/src/helper.cpp:149-165) -- is gathered once into a dense
+		// [rows][k] matrix (im2col) by the elementwise engine; everything else
+		// is multiplied where it lies.
+		struct Operand
+		{
+			const char* base_ = nullptr;
+			int64_t row_ = 0;   // stride along its M / N role
+			int64_t k_ = 0;     // stride along K
+			std::shared_ptr<char> dense_;
+		};
+		auto operand = [&](Operand& out, const PArg& f, const llo_cuda_view& strides,
+			const Role& rows) -> bool
+		{
+			if (merged(rows, strides.stride, out.row_) && merged(rk, strides.stride, out.k_))
+			{
+				out.base_ = f.node_->data_.get() + strides.offset * (int64_t) esize;
+				return true;
+			}
+			if (rk.dims_.size() + rows.dims_.size() > (size_t) R)
+			{
+				return false;
+			}
+			// dense copy with coordinates (k dims..., row dims...): k fastest
+			std::vector<ade::DimT> dims;
+			CoordView pick;   // copy coords -> argument-space coords
+			int pos = 0;
+			const Role* order[2] = {&rk, &rows};
+			for (const Role* role : order)
+			{
+				for (int i : role->dims_)
+				{
+					dims.push_back(n->argshape_.at(i));
+					pick.t_[i].coef_[pos] = 1;
+					++pos;
+				}
+			}
+			ade::Shape dense_shape(dims);
+			PArg gathered = f;
+			gathered.view_ = compose(pick, compose(through, f.view_));
+			normalise(gathered.view_, dense_shape, f.node_->shape_);
+			out.dense_ = materialise(gathered, dense_shape, n->dtype_);
+			out.base_ = out.dense_.get();
+			out.k_ = 1;
+			out.row_ = (int64_t) rk.size_;
+			++stats_.gathers_;
+			return true;
+		};
+		Operand oa, ob;
+		if (false == operand(oa, fa, sa, rm) || false == operand(ob, fb, sb, rn))
+		{
+			return false;
+		}
 		n->data_ = out_buffer(n);
-		const char* A = fa.node_->data_.get() + sa.offset * (int64_t) esize;
-		const char* B = fb.node_->data_.get() + sb.offset * (int64_t) esize;
 		int precision = (age::FLOAT == n->dtype_ && 0 != get_option("tf32x3")) ?
 			LLO_GEMM_3XTF32 : LLO_GEMM_EXACT;
 		device::check(llo_cuda_gemm(device::ctx(), (int) n->dtype_,
-			gm.size_, gn.size_, gk.size_,
-			A, gm.s1_, gk.s1_, B, gk.s2_, gn.s1_,
-			n->data_.get(), gm.any_ ? gm.s2_ : 0, gn.any_ ? gn.s2_ : 0,
-			precision));
+			rm.size_, rn.size_, rk.size_,
+			oa.base_, oa.row_, oa.k_, ob.base_, ob.k_, ob.row_,
+			n->data_.get(), c_m, c_n, precision));
 		++stats_.gemms_;
 		++stats_.fused_;
 		return true;
@@ -1441,6 +1537,16 @@ std::vector<GenericData> planned_eval_many (const ade::TensT& roots,
 	}
 	last_stats = plan.stats_;
 	return outs;
+}
+
+PlanStats plan_preview (const ade::TensT& roots, age::_GENERATED_DTYPE dtype)
+{
+	Plan plan(dtype);
+	for (const ade::TensptrT& root : roots)
+	{
+		plan.build(root.get(), dtype);
+	}
+	return plan.stats_;
 }
 
 GenericData planned_eval (ade::TensptrT root, age::_GENERATED_DTYPE dtype)

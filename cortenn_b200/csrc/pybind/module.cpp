@@ -967,11 +967,25 @@ PYBIND11_MODULE(_C, m)
 			out["programs"] = st.programs_;
 			out["reduces"] = st.reduces_;
 			out["gemms"] = st.gemms_;
+			out["gathers"] = st.gathers_;
 			out["generic"] = st.generic_;
 			out["simplified"] = st.simplified_;
 			out["shared"] = st.shared_;
 			return out;
 		});
+	llo_m.def("plan_preview", [](std::vector<T> roots, py::dtype dtype)
+		{
+			llo::PlanStats st = llo::plan_preview(roots, pyllo::eval_dtype(dtype));
+			py::dict out;
+			out["nodes"] = st.nodes_;
+			out["views"] = st.views_;
+			out["consts"] = st.consts_;
+			out["generic"] = st.generic_;
+			out["simplified"] = st.simplified_;
+			out["shared"] = st.shared_;
+			return out;
+		}, "how the planner classifies the graphs, without evaluating them (no GPU needed)",
+		py::arg("roots"), py::arg("dtype") = py::dtype::of<double>());
 	llo_m.def("set_specialize_min", [](uint64_t elements)
 		{
 			llo::device::check(llo_cuda_set_specialize_min(llo::device::ctx(), elements));

@@ -310,13 +310,57 @@ def test_rand_nodes_draw_per_visit_and_stay_in_range(mode):
     assert vals.min() > 2.0 and vals.max() < 5.0
 
 
-def test_convolution_through_the_general_path(mode):
+def direct_convolution(img, kernel):
+    """numpy VALID cross-correlation: img [batch, w, h, in], kernel [kw, kh, in, out]
+    (what llo/test/ptest.py:441-490 checks against tf.nn.convolution)"""
+    nb, iw, ih, _ = img.shape
+    kw, kh, _, oc = kernel.shape
+    out = np.zeros((nb, iw - kw + 1, ih - kh + 1, oc))
+    for a in range(kw):
+        for b in range(kh):
+            out += np.einsum("nwhc,co->nwho", img[:, a:a + iw - kw + 1, b:b + ih - kh + 1, :], kernel[a, b])
+    return out
+
+
+def test_convolution_lowers_to_one_gathered_gemm(mode):
+    """age.convolution (llo/src/helper.cpp:102-202): PROD of two mapped arguments over a
+    7-d box, summed over (in, kh, kw).  The image's map has two sources per coordinate
+    (h = oh + kh); the planner keeps it as an integer view, gathers the image once into a
+    [rows][k] matrix (im2col) and runs ONE GEMM: no generic per-element functor is left."""
     rng = np.random.default_rng(29)
-    img = llo.variable(rng.uniform(0, 1, (2, 5, 5, 3)), "img")       # [batch, w, h, in]
-    kernel = llo.variable(rng.uniform(0, 1, (3, 3, 3, 4)), "k")      # [kw, kh, in, out]
-    root = age.convolution(img, kernel)
-    check(root, F8, scale_tol=100, what="convolution")
-    check(llo.derive(root, kernel), F8, scale_tol=100, what="d convolution")
+    img = rng.uniform(0, 1, (2, 5, 5, 3))          # [batch, w, h, in]
+    kernel = rng.uniform(0, 1, (3, 3, 3, 4))       # [kw, kh, in, out]
+    vimg, vk = llo.variable(img, "img"), llo.variable(kernel, "k")
+    root = age.convolution(vimg, vk)
+    got = check(root, F8, scale_tol=100, what="convolution")
+    if mode == 1:
+        st = llo.plan_stats()
+        assert st["generic"] == 0 and st["gemms"] == 1 and st["gathers"] == 1, st
+    assert np.abs(got - direct_convolution(img, kernel)).max() <= 1e-12 * np.abs(got).max()
+    check(llo.derive(root, vk), F8, scale_tol=100, what="d convolution / d kernel")
+    if mode == 1:
+        assert llo.plan_stats()["generic"] == 0, llo.plan_stats()
+    # the gradient w.r.t. the image scatters through the reversed two-source map (col2im):
+    # it stays on the generic per-element path, checked against the oracle all the same
+    check(llo.derive(root, vimg), F8, scale_tol=100, what="d convolution / d image")
+
+
+@pytest.mark.parametrize("dtype", [F4, F8])
+def test_convolution_at_a_real_size_matches_a_direct_convolution(dtype):
+    """64 x 64 images, 16 -> 32 channels, 3 x 3 window, batch 8 (wide DimT: the reference's
+    uint8_t dims could not hold the 7-d box): 6.1e8 flop through im2col + the TMA GEMM"""
+    rng = np.random.default_rng(31)
+    img = rng.uniform(-1, 1, (8, 64, 64, 16)).astype(dtype)
+    kernel = rng.uniform(-1, 1, (3, 3, 16, 32)).astype(dtype)
+    root = age.convolution(llo.variable(img, "img"), llo.variable(kernel, "k"))
+    llo.set_option("plan", 1)
+    got = llo.evaluate(root, np.dtype(dtype))
+    st = llo.plan_stats()
+    assert st["generic"] == 0 and st["gemms"] == 1 and st["gathers"] == 1, st
+    want = direct_convolution(img.astype(np.float64), kernel.astype(np.float64))
+    bound = direct_convolution(np.abs(img).astype(np.float64), np.abs(kernel).astype(np.float64))
+    assert got.shape == want.shape
+    assert (np.abs(got - want) <= (1e-6 if dtype == F4 else 1e-12) * bound).all()
 
 
 def test_tf32x3_option_routes_matmul_to_the_tensor_cores():
