@@ -77,6 +77,11 @@ EXPORTS = {
     "llo_cuda_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
     "llo_cuda_wait_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "llo_cuda_sync": (C.c_int, [C.c_void_p]),
+    "llo_cuda_graph_begin": (C.c_int, [C.c_void_p]),
+    "llo_cuda_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "llo_cuda_graph_abort": (C.c_int, [C.c_void_p]),
+    "llo_cuda_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "llo_cuda_graph_destroy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "llo_cuda_launch_count": (C.c_uint64, [C.c_void_p]),
     "llo_cuda_event_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "llo_cuda_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -423,6 +423,70 @@ int llo_cuda_event_destroy (llo_cuda_ctx* ctx, void* event)
 	return LLO_OK;
 }
 
+int llo_cuda_graph_begin (llo_cuda_ctx* ctx)
+{
+	// (relaxed: the calls made while capturing include stream-ordered
+	// allocations and attribute queries that a stricter mode would refuse)
+	LLO_CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+	return LLO_OK;
+}
+
+int llo_cuda_graph_end (llo_cuda_ctx* ctx, void** graph_exec)
+{
+	cudaGraph_t graph = nullptr;
+	cudaError_t err = cudaStreamEndCapture(ctx->stream, &graph);
+	if (cudaSuccess != err || nullptr == graph)
+	{
+		cudaGetLastError();
+		*graph_exec = nullptr;
+		return fail_cuda(cudaSuccess != err ? err : cudaErrorUnknown,
+			"cudaStreamEndCapture (a call made while capturing cannot be captured)");
+	}
+	cudaGraphExec_t exec = nullptr;
+	err = cudaGraphInstantiate(&exec, graph, 0);
+	cudaGraphDestroy(graph);
+	if (cudaSuccess != err)
+	{
+		*graph_exec = nullptr;
+		return fail_cuda(err, "cudaGraphInstantiate");
+	}
+	*graph_exec = (void*) exec;
+	return LLO_OK;
+}
+
+int llo_cuda_graph_abort (llo_cuda_ctx* ctx)
+{
+	cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+	cudaStreamIsCapturing(ctx->stream, &status);
+	if (cudaStreamCaptureStatusNone != status)
+	{
+		cudaGraph_t graph = nullptr;
+		cudaStreamEndCapture(ctx->stream, &graph);
+		if (nullptr != graph)
+		{
+			cudaGraphDestroy(graph);
+		}
+	}
+	cudaGetLastError();
+	return LLO_OK;
+}
+
+int llo_cuda_graph_launch (llo_cuda_ctx* ctx, void* graph_exec, uint64_t launches)
+{
+	LLO_CUDA_TRY(cudaGraphLaunch((cudaGraphExec_t) graph_exec, ctx->stream));
+	ctx->launches += launches;
+	return LLO_OK;
+}
+
+int llo_cuda_graph_destroy (llo_cuda_ctx*, void* graph_exec)
+{
+	if (nullptr != graph_exec)
+	{
+		LLO_CUDA_TRY(cudaGraphExecDestroy((cudaGraphExec_t) graph_exec));
+	}
+	return LLO_OK;
+}
+
 int llo_cuda_seed (llo_cuda_ctx* ctx, uint64_t seed)
 {
 	ctx->seed = seed;

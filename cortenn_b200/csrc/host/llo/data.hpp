@@ -196,6 +196,13 @@ struct Variable final : public ade::iLeaf
 		return (size_t) age::type_size(dtype_) * shape_.n_elems();
 	}
 
+	/// Counter that moves whenever the elements may have changed (anything
+	/// that cached work derived from this leaf compares it)
+	uint64_t version (void) const
+	{
+		return version_;
+	}
+
 	/// Device copy of the elements converted to dtype (uploaded / converted
 	/// only when the host bytes changed since the last call)
 	std::shared_ptr<char> device_data (age::_GENERATED_DTYPE dtype) const;

@@ -92,6 +92,14 @@ struct ShardedOptions
 	/// evaluate on this rank alone whatever the communicator says (the
 	/// single-GPU result a multi-rank run checks itself against)
 	bool solo_ = false;
+
+	/// From the second evaluation on, replay the whole step -- every kernel,
+	/// the stream-ordered allocations of the intermediates, the collectives
+	/// on the second lane -- from ONE CUDA graph (llo_cuda_graph_*), for as
+	/// long as no leaf has been assigned to: the planner and ~40 launches
+	/// per step leave the host's critical path.  Graphs with random draws
+	/// are never captured (a replay would repeat the draw).
+	bool graph_ = true;
 };
 
 /// Gradient evaluation of one loss w.r.t. a set of parameters, summed over
@@ -121,14 +129,47 @@ struct ShardedEvaluator final
 	ade::TensT roots_;
 
 private:
+	/// what a captured step read: a leaf, its version, its device mirror
+	struct LeafState
+	{
+		Variable* leaf_;
+		uint64_t version_;
+		const char* mirror_;
+
+		bool operator == (const LeafState& o) const
+		{
+			return leaf_ == o.leaf_ && version_ == o.version_ && mirror_ == o.mirror_;
+		}
+	};
+
 	struct Layout
 	{
 		GradientPack pack_;
 		std::shared_ptr<char> buffer_;
 		std::vector<std::shared_ptr<char>> slots_;  // aliases into buffer_
+		size_t evals_ = 0;                          // eager evaluations so far
+		std::shared_ptr<void> graph_;               // captured step (cudaGraphExec_t)
+		uint64_t graph_launches_ = 0;
+		std::vector<LeafState> graph_leaves_;
+		long graph_options_ = 0;
 	};
 
 	Layout& layout (age::_GENERATED_DTYPE dtype, bool with_loss);
+
+	/// enqueue one step (plan, kernels, collectives) on the context's stream
+	void enqueue (Layout& lay, age::_GENERATED_DTYPE dtype, bool with_loss);
+
+	std::vector<LeafState> leaf_states (age::_GENERATED_DTYPE dtype);
+
+	std::vector<Variable*> leaves_;
+
+	bool capturable_ = true;    // only Variable leaves, no random draws
+
+public:
+	/// steps replayed from a captured graph so far (tests, bench)
+	size_t replays_ = 0;
+
+private:
 
 	ade::TensT params_;
 

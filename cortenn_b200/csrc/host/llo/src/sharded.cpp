@@ -1,6 +1,7 @@
 #include <unordered_set>
 
 #include "llo/plan.hpp"
+#include "llo/session.hpp"
 #include "llo/sharded.hpp"
 #include "llo/zprune.hpp"
 
@@ -104,6 +105,56 @@ ShardedEvaluator::ShardedEvaluator (ade::TensptrT loss, ade::TensT params,
 	{
 		independent_ = false == reaches(roots_[i].get(), grads);
 	}
+	// what a captured step depends on: every leaf, and whether it may be captured
+	std::unordered_set<ade::iTensor*> seen;
+	std::vector<ade::iTensor*> todo;
+	for (const ade::TensptrT& root : roots_)
+	{
+		todo.push_back(root.get());
+	}
+	while (false == todo.empty())
+	{
+		ade::iTensor* t = todo.back();
+		todo.pop_back();
+		if (false == seen.emplace(t).second)
+		{
+			continue;
+		}
+		if (auto f = dynamic_cast<ade::iFunctor*>(t))
+		{
+			size_t code = f->get_opcode().code_;
+			if (age::RAND_BINO == code || age::RAND_UNIF == code || age::RAND_NORM == code)
+			{
+				capturable_ = false;
+			}
+			for (const ade::MappedTensor& child : f->get_children())
+			{
+				todo.push_back(child.get_tensor().get());
+			}
+		}
+		else if (auto var = dynamic_cast<Variable*>(t))
+		{
+			leaves_.push_back(var);
+		}
+		else
+		{
+			capturable_ = false; // a foreign leaf is copied over on every visit
+		}
+	}
+}
+
+std::vector<ShardedEvaluator::LeafState> ShardedEvaluator::leaf_states (
+	age::_GENERATED_DTYPE dtype)
+{
+	std::vector<LeafState> out;
+	for (Variable* leaf : leaves_)
+	{
+		// (makes the mirror current: uploads and conversions happen here, not
+		// inside a capture; constant leaves are immediates and have no mirror)
+		const char* mirror = leaf->is_filled() ? nullptr : leaf->device_data(dtype).get();
+		out.push_back(LeafState{leaf, leaf->version(), mirror});
+	}
+	return out;
 }
 
 ShardedEvaluator::Layout& ShardedEvaluator::layout (
@@ -154,6 +205,56 @@ std::shared_ptr<char> ShardedEvaluator::grad_eval_device (
 	age::_GENERATED_DTYPE dtype, bool with_loss)
 {
 	Layout& lay = layout(dtype, with_loss);
+	llo_cuda_ctx* ctx = device::ctx();
+	bool use_graph = options_.graph_ && capturable_ && 0 != get_option("plan");
+	if (false == use_graph)
+	{
+		enqueue(lay, dtype, with_loss);
+		return lay.buffer_;
+	}
+	std::vector<LeafState> now = leaf_states(dtype);
+	long opts = get_option("tf32x3") * 2 + get_option("sequential_reduce");
+	if (nullptr != lay.graph_ && now == lay.graph_leaves_ && opts == lay.graph_options_)
+	{
+		device::check(llo_cuda_graph_launch(ctx, lay.graph_.get(), lay.graph_launches_));
+		++replays_;
+		return lay.buffer_;
+	}
+	lay.graph_ = nullptr;
+	if (lay.evals_ < 1)
+	{
+		// the first step runs eagerly: kernels are specialised and loaded, the
+		// scratch arena and the memory pool reach their working size
+		enqueue(lay, dtype, with_loss);
+		++lay.evals_;
+		return lay.buffer_;
+	}
+	uint64_t before = llo_cuda_launch_count(ctx);
+	device::check(llo_cuda_graph_begin(ctx));
+	try
+	{
+		enqueue(lay, dtype, with_loss);
+	}
+	catch (...)
+	{
+		llo_cuda_graph_abort(ctx);
+		throw;
+	}
+	void* exec = nullptr;
+	device::check(llo_cuda_graph_end(ctx, &exec));
+	lay.graph_ = std::shared_ptr<void>(exec,
+		[ctx](void* e) { llo_cuda_graph_destroy(ctx, e); });
+	lay.graph_launches_ = llo_cuda_launch_count(ctx) - before;
+	lay.graph_leaves_ = now;
+	lay.graph_options_ = opts;
+	// nothing ran while capturing: this step is the graph's first launch
+	device::check(llo_cuda_graph_launch(ctx, exec, 0));
+	return lay.buffer_;
+}
+
+void ShardedEvaluator::enqueue (Layout& lay, age::_GENERATED_DTYPE dtype,
+	bool with_loss)
+{
 	llo_cuda_ctx* ctx = device::ctx();
 	size_t esize = age::type_size(dtype);
 	size_t nparams = params_.size();
@@ -225,7 +326,6 @@ std::shared_ptr<char> ShardedEvaluator::grad_eval_device (
 			lay.pack_.count_, (int) dtype, age::SUM,
 			options_.ordered_ ? LLO_ALLREDUCE_ORDERED : LLO_ALLREDUCE_FAST));
 	}
-	return lay.buffer_;
 }
 
 std::vector<GenericData> ShardedEvaluator::grad_eval (

@@ -848,19 +848,22 @@ PYBIND11_MODULE(_C, m)
 
 	py::class_<llo::ShardedEvaluator>(llo_m, "ShardedEvaluator")
 		.def(py::init([](T loss, std::vector<T> params, unsigned passes,
-			bool ordered, bool overlap, bool solo)
+			bool ordered, bool overlap, bool solo, bool graph)
 			{
 				llo::ShardedOptions opts;
 				opts.passes_ = passes;
 				opts.ordered_ = ordered;
 				opts.overlap_ = overlap;
 				opts.solo_ = solo;
+				opts.graph_ = graph;
 				return new llo::ShardedEvaluator(loss, params, opts);
 			}), "gradient evaluation of `loss` w.r.t. `params`, summed over the "
 			"ranks of the communicator (llo/sharded.hpp)",
 			py::arg("loss"), py::arg("params"),
 			py::arg("passes") = (unsigned) llo::OPT_ALL, py::arg("ordered") = false,
-			py::arg("overlap") = true, py::arg("solo") = false)
+			py::arg("overlap") = true, py::arg("solo") = false, py::arg("graph") = true)
+		.def("replays", [](llo::ShardedEvaluator& self) { return self.replays_; },
+			"steps replayed from the captured CUDA graph so far")
 		.def("grad_eval_device", [](llo::ShardedEvaluator& self, py::dtype dtype,
 			bool with_loss)
 			{

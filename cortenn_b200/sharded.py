@@ -106,6 +106,8 @@ class DeviceBackend:
         self.ordered = bool(ordered)
         # LLO_SHARD_OVERLAP=0: one fold after the last gradient (A/B runs)
         self.overlap = bool(overlap) and os.environ.get("LLO_SHARD_OVERLAP", "1") != "0"
+        # LLO_SHARD_GRAPH=0: plan and launch every step instead of replaying a CUDA graph
+        self.graph = os.environ.get("LLO_SHARD_GRAPH", "1") != "0"
         self.solo_rank = bool(solo_rank)
         self._evaluators = {}
 
@@ -127,7 +129,7 @@ class DeviceBackend:
         key = (id(loss), tuple(id(p) for p in params), passes)
         if key not in self._evaluators:
             ev = self.llo.ShardedEvaluator(loss, list(params), passes, self.ordered, self.overlap,
-                                           self.solo_rank)
+                                           self.solo_rank, self.graph)
             self._evaluators[key] = (loss, list(params), ev)     # keeps the ids alive
         return self._evaluators[key][2]
 

@@ -116,6 +116,20 @@ int llo_cuda_memset (llo_cuda_ctx* ctx, void* dst, int byte, size_t bytes);
  * only knows host arrays) */
 int llo_cuda_wait_stream (llo_cuda_ctx* ctx, void* cuda_stream);
 int llo_cuda_sync (llo_cuda_ctx* ctx);
+/* CUDA-graph replay of a fixed sequence of calls on this context (the same
+ * plan over the same buffers, e.g. one gradient evaluation per training step):
+ * llo_cuda_graph_begin starts capturing everything queued on the context's
+ * stream (kernels, stream-ordered allocations and frees, copies, collectives
+ * on the second lane), llo_cuda_graph_end instantiates what was captured,
+ * llo_cuda_graph_launch replays it (`launches` = kernels inside, for
+ * llo_cuda_launch_count).  Nothing runs while capturing.  Calls that
+ * synchronise (h2d / d2h / sync) must not be made between begin and end;
+ * llo_cuda_graph_abort ends a capture that went wrong. */
+int llo_cuda_graph_begin (llo_cuda_ctx* ctx);
+int llo_cuda_graph_end (llo_cuda_ctx* ctx, void** graph_exec);
+int llo_cuda_graph_abort (llo_cuda_ctx* ctx);
+int llo_cuda_graph_launch (llo_cuda_ctx* ctx, void* graph_exec, uint64_t launches);
+int llo_cuda_graph_destroy (llo_cuda_ctx* ctx, void* graph_exec);
 /* number of kernels this context has launched so far (bench `gpu_launches`) */
 uint64_t llo_cuda_launch_count (llo_cuda_ctx* ctx);
 /* CUDA events on the context's stream, for device-side timing */

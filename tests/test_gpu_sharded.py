@@ -82,6 +82,40 @@ def test_native_pack_layout_matches_the_python_mirror():
         np.testing.assert_array_equal(np.asarray(g).reshape(want.shape), want)
 
 
+def test_steps_replay_from_a_cuda_graph_until_a_leaf_changes():
+    """from the second evaluation on the whole step is one cudaGraphLaunch; assigning to a
+    leaf (new version, new mirror) makes the next step plan and capture again"""
+    X, Y, params = workloads.mlp_data(64, (24, 32, 16, 6), F4)
+    loss, pvars, (vx, vy) = workloads.mlp_graph(age, llo, X, Y, params)
+    eager = llo.ShardedEvaluator(loss, pvars, graph=False)
+    want = eager.grad_eval(np.dtype(F4), True)
+    ev = llo.ShardedEvaluator(loss, pvars)
+    first = ev.grad_eval(np.dtype(F4), True)           # eager warm-up
+    assert ev.replays() == 0
+    second = ev.grad_eval(np.dtype(F4), True)          # captured, launched once
+    before = llo.launch_count()
+    third = ev.grad_eval(np.dtype(F4), True)           # replayed
+    assert ev.replays() == 1
+    assert llo.launch_count() - before > 10            # the replay's kernels are counted
+    for w, a, b, c in zip(want, first, second, third):
+        np.testing.assert_array_equal(w, a)
+        np.testing.assert_array_equal(w, b)
+        np.testing.assert_array_equal(w, c)
+    # new inputs: the graph is stale, the step is planned again and matches a fresh evaluator
+    X2 = (X * 0.5 + 0.1).astype(F4)
+    vx.assign(X2)
+    got = ev.grad_eval(np.dtype(F4), True)
+    assert ev.replays() == 1
+    again = ev.grad_eval(np.dtype(F4), True)
+    assert ev.replays() == 2
+    fresh = eager.grad_eval(np.dtype(F4), True)
+    want_loss, want_grads = workloads.mlp_reference_gradients(X2, Y, params)
+    assert abs(float(got[0]) - want_loss) <= 2e-5 * abs(want_loss)
+    for f, g, a in zip(fresh, got, again):
+        np.testing.assert_array_equal(f, g)
+        np.testing.assert_array_equal(f, a)
+
+
 def test_device_buffer_round_trip_and_world1_allreduce():
     buf = llo.DeviceBuffer(64 * 4)
     data = np.arange(64, dtype=F4)
