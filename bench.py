@@ -733,6 +733,16 @@ def run_own(args, rank, local_rank, world):
     if not llo.available():
         raise RuntimeError("bench.py: no usable B200 and there is no CPU fallback")
     timer = Timer(llo, capi, dist, torch)
+    if args.mlp_only:
+        res = mlp_workload(args, timer, age, llo, rank, world, max(3, min(args.steps, 10)), 3,
+                           not args.skip_verify)
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+        if dist is not None:
+            timer.barrier()
+            llo.comm_destroy()
+            dist.destroy_process_group()
+        return
 
     side = 1 << (args.log2n // 2)
     x, b = workloads.chain_inputs(side, seed_x=2 + rank)
@@ -885,6 +895,8 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-side", action="store_true", help="skip the reduce / matmul workloads")
     ap.add_argument("--skip-mlp", action="store_true")
+    ap.add_argument("--mlp-only", action="store_true",
+                    help="time only the batch-sharded MLP (experiments; prints its block, not the contract line)")
     ap.add_argument("--skip-verify", action="store_true", help="do not compare the timed outputs with float64 numpy")
     ap.add_argument("--no-traffic-probe", action="store_true", help="do not run the ncu DRAM-bytes pass")
     ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)

@@ -518,6 +518,60 @@ int drive (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A,
 		}
 		return LLO_OK;
 	}
+	args.tail_splits = 1;
+	args.full_tiles = (uint32_t) tiles;
+	args.ktiles = ktiles;
+	args.part = nullptr;
+	// Units mode (kernels that take it: DUAL > 1 marks the fp32 tile kernel):
+	// with more tiles than CTA slots the last wave may be mostly empty (512
+	// tiles on 296 slots: 216 of 296).  Its tiles are then cut along k so that
+	// they fill the slots as the whole tiles drain.  Cost in k-tile times of
+	// the tail: slots-fuls of units x (k-tiles per unit + 1) against
+	// (k-tiles + 1) for leaving it whole.
+	if (DUAL > 1 && false == ak && false == bk && nullptr == std::getenv("LLO_GEMM_NO_UNITS"))
+	{
+		uint64_t slots = (uint64_t) ctx->sm_count * DUAL;
+		uint64_t rest = tiles % slots;
+		if (tiles > slots && 0 != rest && rest * 100 < slots * 85 && ktiles >= 8)
+		{
+			uint64_t best = (uint64_t) ktiles + 1;
+			uint32_t chosen = 1;
+			for (uint64_t cand = 2; cand <= std::min<uint64_t>(ktiles / 3, 16); ++cand)
+			{
+				uint64_t per = (ktiles + cand - 1) / cand;
+				uint64_t real = (ktiles + per - 1) / per;
+				uint64_t c = (rest * real + slots - 1) / slots * (per + 1) + 1;
+				if (c * 100 < best * 92)
+				{
+					best = c;
+					chosen = (uint32_t) real;
+				}
+			}
+			if (chosen > 1)
+			{
+				args.kt_per_split = (ktiles + chosen - 1) / chosen;
+				args.tail_splits = (ktiles + args.kt_per_split - 1) / args.kt_per_split;
+				args.full_tiles = (uint32_t) (tiles - rest);
+				args.split_stride = 0;
+				args.C = C;
+				args.c_rs = p.c_rs;
+				args.vec_store = (0 == ((uintptr_t) C & (uintptr_t) (need * sizeof(T) - 1)) &&
+					0 == p.c_rs % need) ? 1 : 0;
+				void* ws = nullptr;
+				LLO_TRY(scratch.get(&ws, (size_t) rest * args.tail_splits * BM * BN * sizeof(T)));
+				args.part = (T*) ws;
+				handled = true;
+				LLO_TRY(launch(ak, bk, ma, mb, args, 0));
+				int64_t unit = (int64_t) (16 / sizeof(T));
+				uint32_t vec = (0 == ((uintptr_t) C & 15u) && 0 == p.c_rs % unit) ? 1 : 0;
+				tile_fold_kernel<T,BM,BN><<<dim3((unsigned) rest, 8), 256, 0, ctx->stream>>>(
+					C, p.c_rs, args.part, (uint32_t) p.M, (uint32_t) p.N,
+					args.tiles_m, args.tiles_n, args.full_tiles, args.tail_splits, vec);
+				LLO_TRY(launched(ctx, "tile_fold_kernel"));
+				return LLO_OK;
+			}
+		}
+	}
 	// split-K: the k-tiles of every output tile may be spread over `splits`
 	// CTAs (partial products summed in split order by a second pass) when
 	// that fills the SMs better.  Cost model in k-tile times: waves of CTAs

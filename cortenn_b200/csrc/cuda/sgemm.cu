@@ -603,15 +603,35 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 
 	// tile order: walk GROUP tile-rows per tile-column so the CTAs in flight
 	// share their A panels and B panels in L2
-	constexpr uint32_t GROUP = 16;
 	uint32_t bid = blockIdx.x;
-	uint32_t per_group = GROUP * args.tiles_n;
-	uint32_t first_m = (bid / per_group) * GROUP;
-	uint32_t gsize = min(args.tiles_m - first_m, GROUP);
-	uint32_t tile_m = first_m + (bid % per_group) % gsize;
-	uint32_t tile_n = (bid % per_group) / gsize;
+	uint32_t tile_m, tile_n;
 	uint32_t kt_begin = blockIdx.y * args.kt_per_split;
 	uint32_t ktiles = min((args.K + BK - 1) / BK - kt_begin, args.kt_per_split);
+	// Units mode (tail_splits > 1, a 1-D grid): the first full_tiles CTAs are
+	// whole tiles -- whole waves of the chip --, the tiles of the last, partly
+	// empty wave are cut along k into tail_splits CTAs each, which the
+	// hardware hands out as slots free up; their partial tiles are summed in
+	// split order by tile_fold_kernel.
+	float* part_tile = nullptr;
+	if (args.tail_splits > 1)
+	{
+		uint32_t tile = bid;
+		kt_begin = 0;
+		ktiles = args.ktiles;
+		if (bid >= args.full_tiles)
+		{
+			uint32_t t = bid - args.full_tiles;
+			tile = args.full_tiles + t / args.tail_splits;
+			kt_begin = (t % args.tail_splits) * args.kt_per_split;
+			ktiles = min(args.ktiles - kt_begin, args.kt_per_split);
+			part_tile = args.part + (size_t) t * (BM * BN);
+		}
+		tile_coords(tile, args.tiles_m, args.tiles_n, tile_m, tile_n);
+	}
+	else
+	{
+		tile_coords(bid, args.tiles_m, args.tiles_n, tile_m, tile_n);
+	}
 
 	int warp = threadIdx.x >> 5;
 	int lane = threadIdx.x & 31;
@@ -849,6 +869,35 @@ sgemm_tma_kernel (const __grid_constant__ CUtensorMap map_a,
 	}
 	float acc[8][8];
 	unpack8x8<PAIR_I>(acc, acc2);
+	if (nullptr != part_tile)
+	{
+		// partial product of a tail tile: dense [BM][BN], always in range
+		float* ptile = part_tile + (wm * 64) * BN + wn * 32;
+#pragma unroll
+		for (int i = 0; i < 8; ++i)
+		{
+			float* prow = ptile + row_of<AK>(tm, i) * BN;
+			if (BKC)
+			{
+#pragma unroll
+				for (int j = 0; j < 8; j += 2)
+				{
+					*(float2*) (prow + col_of<true>(tn, j)) =
+						make_float2(acc[i][j], acc[i][j + 1]);
+				}
+			}
+			else
+			{
+#pragma unroll
+				for (int j = 0; j < 8; j += 4)
+				{
+					*(float4*) (prow + col_of<false>(tn, j)) = make_float4(
+						acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+				}
+			}
+		}
+		return;
+	}
 	uint32_t m_base = tile_m * BM + wm * 64;
 	uint32_t n_base = tile_n * BN + wn * 32;
 #pragma unroll
@@ -928,6 +977,12 @@ int launch_variant (llo_cuda_ctx* ctx, const CUtensorMap& ma,
 	LLO_CUDA_TRY(cudaFuncSetAttribute(sgemm_tma_kernel<AK,BKC>,
 		cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	dim3 grid(args.tiles_m * args.tiles_n, splits);
+	if (0 == splits)
+	{
+		// units mode: whole tiles, then the k-split tiles of the last wave
+		grid = dim3(args.full_tiles + (args.tiles_m * args.tiles_n - args.full_tiles) *
+			args.tail_splits, 1);
+	}
 	sgemm_tma_kernel<AK,BKC><<<grid, THREADS, smem, ctx->stream>>>(ma, mb, args);
 	return launched(ctx, "sgemm_tma_kernel");
 }
