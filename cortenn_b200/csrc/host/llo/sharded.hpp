@@ -147,7 +147,9 @@ private:
 		GradientPack pack_;
 		std::shared_ptr<char> buffer_;
 		std::vector<std::shared_ptr<char>> slots_;  // aliases into buffer_
-		size_t evals_ = 0;                          // eager evaluations so far
+		size_t evals_ = 0;                          // eager evaluations with warm_options_
+		long warm_options_ = -1;
+		bool no_graph_ = false;                     // a capture failed: stay eager
 		std::shared_ptr<void> graph_;               // captured step (cudaGraphExec_t)
 		uint64_t graph_launches_ = 0;
 		std::vector<LeafState> graph_leaves_;

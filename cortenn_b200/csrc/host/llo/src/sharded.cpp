@@ -206,7 +206,8 @@ std::shared_ptr<char> ShardedEvaluator::grad_eval_device (
 {
 	Layout& lay = layout(dtype, with_loss);
 	llo_cuda_ctx* ctx = device::ctx();
-	bool use_graph = options_.graph_ && capturable_ && 0 != get_option("plan");
+	bool use_graph = options_.graph_ && capturable_ && false == lay.no_graph_ &&
+		0 != get_option("plan");
 	if (false == use_graph)
 	{
 		enqueue(lay, dtype, with_loss);
@@ -221,27 +222,41 @@ std::shared_ptr<char> ShardedEvaluator::grad_eval_device (
 		return lay.buffer_;
 	}
 	lay.graph_ = nullptr;
+	if (opts != lay.warm_options_)
+	{
+		lay.warm_options_ = opts;
+		lay.evals_ = 0;
+	}
 	if (lay.evals_ < 1)
 	{
-		// the first step runs eagerly: kernels are specialised and loaded, the
-		// scratch arena and the memory pool reach their working size
+		// the first step under a set of options runs eagerly: kernels are
+		// specialised and loaded, the scratch arena and the memory pool reach
+		// their working size (none of which may happen inside a capture)
 		enqueue(lay, dtype, with_loss);
 		++lay.evals_;
 		return lay.buffer_;
 	}
 	uint64_t before = llo_cuda_launch_count(ctx);
 	device::check(llo_cuda_graph_begin(ctx));
+	void* exec = nullptr;
+	bool captured = true;
 	try
 	{
 		enqueue(lay, dtype, with_loss);
+		device::check(llo_cuda_graph_end(ctx, &exec));
 	}
-	catch (...)
+	catch (const std::exception&)
 	{
+		// something in the step cannot be captured: stay eager from here on
 		llo_cuda_graph_abort(ctx);
-		throw;
+		captured = false;
 	}
-	void* exec = nullptr;
-	device::check(llo_cuda_graph_end(ctx, &exec));
+	if (false == captured || nullptr == exec)
+	{
+		lay.no_graph_ = true;
+		enqueue(lay, dtype, with_loss);
+		return lay.buffer_;
+	}
 	lay.graph_ = std::shared_ptr<void>(exec,
 		[ctx](void* e) { llo_cuda_graph_destroy(ctx, e); });
 	lay.graph_launches_ = llo_cuda_launch_count(ctx) - before;
