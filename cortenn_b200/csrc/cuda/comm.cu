@@ -13,6 +13,8 @@
 
 #include <dlfcn.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace llo_cuda
@@ -247,7 +249,15 @@ int llo_cuda_allreduce_async (llo_cuda_ctx* ctx, void* buf, uint64_t n,
 	if (nullptr == ctx->comm_stream)
 	{
 		LLO_CUDA_TRY(cudaSetDevice(ctx->device));
-		LLO_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+		// highest priority: the collective's few CTAs take the first SM slots
+		// that free up instead of queueing behind every CTA of the GEMM
+		// launched beside it (LLO_COMM_PRIORITY=0: experiments only)
+		int lowest = 0, highest = 0;
+		LLO_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lowest, &highest));
+		const char* env = std::getenv("LLO_COMM_PRIORITY");
+		int priority = (nullptr != env && 0 == std::atoi(env)) ? lowest : highest;
+		LLO_CUDA_TRY(cudaStreamCreateWithPriority(&ctx->comm_stream,
+			cudaStreamNonBlocking, priority));
 		LLO_CUDA_TRY(cudaEventCreateWithFlags(&ctx->comm_ready, cudaEventDisableTiming));
 		LLO_CUDA_TRY(cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming));
 	}

@@ -86,8 +86,22 @@ struct ShardedOptions
 	/// bit-identical sums on every rank, not overlapped
 	bool ordered_ = false;
 
-	/// start each gradient's fold as soon as it is computed (backward order)
+	/// start each gradient's fold as soon as it is computed
 	bool overlap_ = true;
+
+	/// Evaluation order of the gradients when the folds overlap.
+	/// true : the FIRST parameters' gradients first.  Their derivative chain
+	///        runs through every layer, so the forward pass and the whole
+	///        backward chain -- the big persistent GEMMs, one CTA per SM with a
+	///        fixed unit schedule, which a collective's CTAs landing on some SMs
+	///        would delay as a whole -- finish before the first fold starts;
+	///        the folds then run beside the per-layer weight-gradient GEMMs,
+	///        whose CTAs the hardware hands out as slots free up.
+	/// false: backward order (last layer's gradients first, each fold starts
+	///        as early as possible, beside the rest of the chain).
+	/// Measured at 8 GPUs, MLP 784-1024-1024-10 / batch 65536: backward order
+	/// 1.933 ms -- slower than no overlap at all, 1.887 ms (tools/_ab/n8_prio.sh).
+	bool deep_first_ = true;
 
 	/// evaluate on this rank alone whatever the communicator says (the
 	/// single-GPU result a multi-rank run checks itself against)

@@ -1,3 +1,4 @@
+#include <algorithm>
 #include <unordered_set>
 
 #include "llo/plan.hpp"
@@ -277,9 +278,9 @@ void ShardedEvaluator::enqueue (Layout& lay, age::_GENERATED_DTYPE dtype,
 	bool overlap = many && options_.overlap_ && false == options_.ordered_ &&
 		independent_ && nparams > 0;
 
-	// evaluation order = backward order: the loss, then the gradients of the
-	// LAST parameters first (they are complete first, the derivative chain
-	// reaches the first layer last)
+	// evaluation order: the loss, then the gradients -- of the first
+	// parameters first (deep_first_, see ShardedOptions) or of the last
+	// parameters first (backward order: they are complete first)
 	ade::TensT roots;
 	std::vector<std::shared_ptr<char>> dests;
 	std::vector<size_t> slot_of;
@@ -289,8 +290,10 @@ void ShardedEvaluator::enqueue (Layout& lay, age::_GENERATED_DTYPE dtype,
 		dests.push_back(lay.slots_[0]);
 		slot_of.push_back(0);
 	}
-	for (size_t k = nparams; k-- > 0;)
+	bool deep = overlap && options_.deep_first_;
+	for (size_t j = 0; j < nparams; ++j)
 	{
+		size_t k = deep ? j : nparams - 1 - j;
 		size_t slot = k + (with_loss ? 1 : 0);
 		roots.push_back(roots_[1 + k]);
 		dests.push_back(lay.slots_[slot]);
@@ -298,7 +301,8 @@ void ShardedEvaluator::enqueue (Layout& lay, age::_GENERATED_DTYPE dtype,
 	}
 	// Buckets: slots are contiguous in the buffer, so a run of roots that is
 	// complete folds with one call.  Two gradients (weights + bias of a
-	// layer) per bucket keeps the calls few; the loss joins the last bucket.
+	// layer) per bucket keeps the calls few; the loss (slot 0, evaluated
+	// first) joins the bucket that holds slot 1.
 	size_t first_grad = with_loss ? 1 : 0;
 	std::function<void(size_t)> on_done = nullptr;
 	if (overlap)
@@ -307,19 +311,19 @@ void ShardedEvaluator::enqueue (Layout& lay, age::_GENERATED_DTYPE dtype,
 		{
 			if (i < first_grad)
 			{
-				return; // the loss travels with the last bucket
+				return; // the loss travels with a gradient bucket
 			}
-			size_t g = i - first_grad;       // g-th gradient in backward order
+			size_t g = i - first_grad;       // g-th gradient in evaluation order
 			bool last = g + 1 == nparams;
 			if (0 == g % 2 && false == last)
 			{
 				return; // first of a pair: wait for its partner
 			}
-			// backward order walks the slots downwards: this root has the
-			// lowest slot of its bucket, the bucket's first root the highest
-			size_t lo_slot = slot_of[i];
-			size_t hi_slot = slot_of[i - g % 2];
-			if (last && with_loss)
+			size_t a_slot = slot_of[i];
+			size_t b_slot = slot_of[i - g % 2];
+			size_t lo_slot = std::min(a_slot, b_slot);
+			size_t hi_slot = std::max(a_slot, b_slot);
+			if (with_loss && 1 == lo_slot)
 			{
 				lo_slot = 0;
 			}

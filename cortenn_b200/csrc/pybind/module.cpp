@@ -848,7 +848,7 @@ PYBIND11_MODULE(_C, m)
 
 	py::class_<llo::ShardedEvaluator>(llo_m, "ShardedEvaluator")
 		.def(py::init([](T loss, std::vector<T> params, unsigned passes,
-			bool ordered, bool overlap, bool solo, bool graph)
+			bool ordered, bool overlap, bool solo, bool graph, bool deep_first)
 			{
 				llo::ShardedOptions opts;
 				opts.passes_ = passes;
@@ -856,12 +856,14 @@ PYBIND11_MODULE(_C, m)
 				opts.overlap_ = overlap;
 				opts.solo_ = solo;
 				opts.graph_ = graph;
+				opts.deep_first_ = deep_first;
 				return new llo::ShardedEvaluator(loss, params, opts);
 			}), "gradient evaluation of `loss` w.r.t. `params`, summed over the "
 			"ranks of the communicator (llo/sharded.hpp)",
 			py::arg("loss"), py::arg("params"),
 			py::arg("passes") = (unsigned) llo::OPT_ALL, py::arg("ordered") = false,
-			py::arg("overlap") = true, py::arg("solo") = false, py::arg("graph") = true)
+			py::arg("overlap") = true, py::arg("solo") = false, py::arg("graph") = true,
+			py::arg("deep_first") = true)
 		.def("replays", [](llo::ShardedEvaluator& self) { return self.replays_; },
 			"steps replayed from the captured CUDA graph so far")
 		.def("grad_eval_device", [](llo::ShardedEvaluator& self, py::dtype dtype,

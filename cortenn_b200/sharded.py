@@ -108,6 +108,9 @@ class DeviceBackend:
         self.overlap = bool(overlap) and os.environ.get("LLO_SHARD_OVERLAP", "1") != "0"
         # LLO_SHARD_GRAPH=0: plan and launch every step instead of replaying a CUDA graph
         self.graph = os.environ.get("LLO_SHARD_GRAPH", "1") != "0"
+        # LLO_SHARD_ORDER=backward: last layer's gradients (and their folds) first; the default
+        # evaluates the first layer's gradients first, see llo/sharded.hpp deep_first_
+        self.deep_first = os.environ.get("LLO_SHARD_ORDER", "deep") != "backward"
         self.solo_rank = bool(solo_rank)
         self._evaluators = {}
 
@@ -129,7 +132,7 @@ class DeviceBackend:
         key = (id(loss), tuple(id(p) for p in params), passes)
         if key not in self._evaluators:
             ev = self.llo.ShardedEvaluator(loss, list(params), passes, self.ordered, self.overlap,
-                                           self.solo_rank, self.graph)
+                                           self.solo_rank, self.graph, self.deep_first)
             self._evaluators[key] = (loss, list(params), ev)     # keeps the ids alive
         return self._evaluators[key][2]
 

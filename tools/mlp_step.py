@@ -18,9 +18,12 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--tf32x3", action="store_true")
     ap.add_argument("--trace", action="store_true")
+    ap.add_argument("--recompute", type=int, default=-1)
     args = ap.parse_args()
     if args.tf32x3:
         llo.set_option("tf32x3", 1)
+    if args.recompute >= 0:
+        llo.set_option("recompute", args.recompute)
     X, Y, params = workloads.mlp_data(args.batch)
     ex = BatchShardedExecutor(args.batch, rank=0, world=1)
     loss, pvars, _ = workloads.mlp_graph(age, llo, ex.shard(X), ex.shard(Y), params, global_batch=args.batch)
