@@ -18,6 +18,7 @@
 ///
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include <utility>
 
@@ -36,6 +37,74 @@ __device__ __forceinline__ T fma_t (T a, T b, T c)
 {
 	if constexpr (sizeof(T) == 4) { return fmaf(a, b, c); }
 	else { return fma(a, b, c); }
+}
+
+// packed fp32 FMA (SASS FFMA2, see sgemm.cu): two IEEE fmaf per issue slot; a
+// pair built from one scalar twice folds into the broadcast operand form
+using f32x2 = unsigned long long;
+
+__device__ __forceinline__ f32x2 pack2 (float lo, float hi)
+{
+	f32x2 r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+
+__device__ __forceinline__ void unpack2 (f32x2 v, float& lo, float& hi)
+{
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+__device__ __forceinline__ void fma2 (f32x2& acc, f32x2 a, f32x2 b)
+{
+	asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+/// Sum C values per lane over the 32 lanes with the xor tree 16, 8, 4, 2, 1.
+/// While the count is even a stage HALVES it: partners swap the halves they do
+/// not keep, so a stage costs C / 2 shuffles instead of C and the tree as a
+/// whole ~C instead of 5 C.  Every sum is the same tree of the same operands as
+/// the plain all-lanes butterfly (a + b == b + a), i.e. bit-identical to it.
+/// On return the lane holds elements [base, base + reduced_count<C, 16>()) in
+/// v[0 ..]; `owner` is false on lanes that hold a duplicate.
+template <int C, int BIT>
+constexpr int reduced_count (void)
+{
+	if constexpr (BIT < 1) { return C; }
+	else if constexpr (0 == C % 2) { return reduced_count<C / 2, BIT / 2>(); }
+	else { return reduced_count<C, BIT / 2>(); }
+}
+
+template <typename T, int C0, int C, int BIT>
+__device__ __forceinline__ void halving_tree (T (&v)[C0], int lane, int& base, bool& owner)
+{
+	if constexpr (BIT >= 1)
+	{
+		const bool upper = 0 != (lane & BIT);
+		if constexpr (0 == C % 2)
+		{
+			constexpr int H = C / 2;
+#pragma unroll
+			for (int j = 0; j < H; ++j)
+			{
+				T mine = upper ? v[H + j] : v[j];
+				T send = upper ? v[j] : v[H + j];
+				v[j] = mine + __shfl_xor_sync(0xffffffffu, send, BIT);
+			}
+			base += upper ? H : 0;
+			halving_tree<T,C0,H,BIT / 2>(v, lane, base, owner);
+		}
+		else
+		{
+#pragma unroll
+			for (int j = 0; j < C; ++j)
+			{
+				v[j] = v[j] + __shfl_xor_sync(0xffffffffu, v[j], BIT);
+			}
+			owner = owner && false == upper;
+			halving_tree<T,C0,C,BIT / 2>(v, lane, base, owner);
+		}
+	}
 }
 
 // ---- skinny output, A rows contiguous along k: a warp per R rows at a time -------
@@ -64,6 +133,15 @@ constexpr int skinny_rows_r (void)
 	return (int) sizeof(T) * NN <= 48 ? 4 : ((int) sizeof(T) * NN <= 96 ? 2 : 1);
 }
 
+/// shared-memory words of B for `k` staged k's: blocks of E k's x NN columns
+/// (one block = what a lane multiplies per step), each followed by 16 bytes so
+/// that the 8 lanes of a quarter warp hit 8 different 16-byte bank groups
+template <typename T, int NN>
+__host__ __device__ constexpr uint32_t skinny_block (void)
+{
+	return (uint32_t) (16 / sizeof(T)) * NN + (uint32_t) (16 / sizeof(T));
+}
+
 template <typename T, int NN>
 __global__ void __launch_bounds__(256, 2)
 skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
@@ -71,12 +149,13 @@ skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
 {
 	constexpr int R = skinny_rows_r<T,NN>();
 	constexpr int E = 16 / (int) sizeof(T);
+	constexpr uint32_t BLOCK = skinny_block<T,NN>();
+	constexpr bool F32 = 4 == sizeof(T);
 	using V = typename std::conditional<8 == sizeof(T), double2, float4>::type;
-	// B is staged `kcap` k's at a time (all of it when it fits: K x NN elements),
-	// transposed: bs[n][pitch]
+	// B is staged `kcap` k's at a time (all of it when it fits), k-major:
+	// bs[k / E][k % E][n], see skinny_block
 	extern __shared__ __align__(16) unsigned char skinny_smem[];
 	T* bs = reinterpret_cast<T*>(skinny_smem);
-	const uint32_t pitch = kcap + E;
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	const int N = (int) p.N;
@@ -90,14 +169,18 @@ skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
 	{
 	const uint64_t row0 = (group * 8 + warp) * R;
 	const bool live = row0 < p.M;
-	T acc[R][NN];
+	// fp32: pairs of neighbouring columns share an FFMA2 (B's row vectors hold
+	// them in consecutive registers, A's value is the broadcast operand)
+	T acc[F32 ? 1 : R][F32 ? 1 : NN];
+	f32x2 acc2[F32 ? R : 1][F32 ? NN / 2 : 1];
 #pragma unroll
 	for (int r = 0; r < R; ++r)
 	{
 #pragma unroll
 		for (int n = 0; n < NN; ++n)
 		{
-			acc[r][n] = T(0);
+			if constexpr (F32) { acc2[r][n / 2] = 0ull; }
+			else { acc[r][n] = T(0); }
 		}
 	}
 	const T* rowp[R];
@@ -114,16 +197,15 @@ skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
 		if (kcap < K || group == blockIdx.x)
 		{
 		__syncthreads();
-		// thread = one k: consecutive threads write consecutive words of every
-		// bs row (no bank conflicts) and read neighbouring rows of B (zero
-		// beyond N / len)
+		// thread = one k (zero beyond N / len)
 		for (uint32_t k = threadIdx.x; k < padded; k += 256)
 		{
 			const T* brow = B + (int64_t) (kc + k) * p.b_rs;
+			T* dst = bs + (k / E) * BLOCK + (k % E) * NN;
 #pragma unroll
 			for (int n = 0; n < NN; ++n)
 			{
-				bs[n * pitch + k] = (n < N && k < len) ?
+				dst[n] = (n < N && k < len) ?
 					__ldg(brow + (int64_t) n * p.b_cs) : T(0);
 			}
 		}
@@ -163,20 +245,37 @@ skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
 				}
 			}
 		};
+		// one step: the lane's E consecutive k against every column, k ascending
 		auto multiply = [&] (const T (&a)[R][E], uint32_t k0)
 		{
+			const V* blk = reinterpret_cast<const V*>(bs + (k0 / E) * BLOCK);
 #pragma unroll
-			for (int n = 0; n < NN; ++n)
+			for (int e = 0; e < E; ++e)
 			{
-				V bv = *reinterpret_cast<const V*>(bs + n * pitch + k0);
-				const T* bt = reinterpret_cast<const T*>(&bv);
 #pragma unroll
-				for (int e = 0; e < E; ++e)
+				for (int q = 0; q < NN / E; ++q)
 				{
-#pragma unroll
-					for (int r = 0; r < R; ++r)
+					V bv = blk[e * (NN / E) + q];
+					if constexpr (F32)
 					{
-						acc[r][n] = fma_t(a[r][e], bt[e], acc[r][n]);
+						f32x2 b01 = pack2(bv.x, bv.y);
+						f32x2 b23 = pack2(bv.z, bv.w);
+#pragma unroll
+						for (int r = 0; r < R; ++r)
+						{
+							f32x2 ar = pack2(a[r][e], a[r][e]);
+							fma2(acc2[r][2 * q], ar, b01);
+							fma2(acc2[r][2 * q + 1], ar, b23);
+						}
+					}
+					else
+					{
+#pragma unroll
+						for (int r = 0; r < R; ++r)
+						{
+							acc[r][2 * q] = fma_t(a[r][e], (T) bv.x, acc[r][2 * q]);
+							acc[r][2 * q + 1] = fma_t(a[r][e], (T) bv.y, acc[r][2 * q + 1]);
+						}
 					}
 				}
 			}
@@ -204,25 +303,42 @@ skinny_rows_kernel (T* __restrict__ C, const T* __restrict__ A,
 			}
 		}
 	}
-	if (false == live)
-	{
-		continue;
-	}
+	// the 32 per-lane sums of each output fold through the xor tree; every
+	// warp of the CTA takes part (shuffles need all lanes), dead ones write nothing
+	T v[R * NN];
 #pragma unroll
 	for (int r = 0; r < R; ++r)
 	{
 #pragma unroll
 		for (int n = 0; n < NN; ++n)
 		{
-			T v = acc[r][n];
-#pragma unroll
-			for (int off = 16; off > 0; off >>= 1)
+			if constexpr (F32)
 			{
-				v = v + __shfl_xor_sync(0xffffffffu, v, off);
+				if (0 == n % 2)
+				{
+					unpack2(acc2[r][n / 2], v[r * NN + n], v[r * NN + n + 1]);
+				}
 			}
-			if (0 == lane && row0 + r < p.M && n < N)
+			else
 			{
-				C[(int64_t) (row0 + r) * p.c_rs + (int64_t) n * p.c_cs] = v;
+				v[r * NN + n] = acc[r][n];
+			}
+		}
+	}
+	int base = 0;
+	bool owner = true;
+	halving_tree<T,R * NN,R * NN,16>(v, lane, base, owner);
+	if (live && owner)
+	{
+		constexpr int LEFT = reduced_count<R * NN,16>();
+#pragma unroll
+		for (int t = 0; t < LEFT; ++t)
+		{
+			int r = (base + t) / NN;
+			int n = (base + t) % NN;
+			if (row0 + r < p.M && n < N)
+			{
+				C[(int64_t) (row0 + r) * p.c_rs + (int64_t) n * p.c_cs] = v[t];
 			}
 		}
 	}
@@ -253,16 +369,52 @@ skinny_cols_kernel (T* __restrict__ part, const T* __restrict__ A,
 	const int N = (int) p.N;
 	uint32_t k_begin = blockIdx.y * k_per_block;
 	uint32_t k_end = min((uint32_t) p.K, k_begin + k_per_block);
-	T acc[E][NN];
+	// fp32: the lane's neighbouring rows (m, m + 1) share an FFMA2 -- they sit
+	// in consecutive registers of the 128-bit load, B's value is the broadcast
+	constexpr bool F32 = 4 == sizeof(T);
+	T acc[F32 ? 1 : E][F32 ? 1 : NN];
+	f32x2 acc2[F32 ? E / 2 : 1][F32 ? NN : 1];
 #pragma unroll
 	for (int e = 0; e < E; ++e)
 	{
 #pragma unroll
 		for (int n = 0; n < NN; ++n)
 		{
-			acc[e][n] = T(0);
+			if constexpr (F32) { acc2[e / 2][n] = 0ull; }
+			else { acc[e][n] = T(0); }
 		}
 	}
+	// one k: every column of B's row (read as 128-bit vectors, all lanes the
+	// same address: broadcasts) against the lane's E rows
+	auto multiply = [&] (const T (&a)[E], const T* brow)
+	{
+		const V* bq = reinterpret_cast<const V*>(brow);
+#pragma unroll
+		for (int q = 0; q < NN / E; ++q)
+		{
+			V bv = bq[q];
+			const T* bt = reinterpret_cast<const T*>(&bv);
+#pragma unroll
+			for (int i = 0; i < E; ++i)
+			{
+				int n = q * E + i;
+				if constexpr (F32)
+				{
+					f32x2 bb = pack2(bt[i], bt[i]);
+					fma2(acc2[0][n], pack2(a[0], a[1]), bb);
+					fma2(acc2[1][n], pack2(a[2], a[3]), bb);
+				}
+				else
+				{
+#pragma unroll
+					for (int e = 0; e < E; ++e)
+					{
+						acc[e][n] = fma_t(a[e], bt[i], acc[e][n]);
+					}
+				}
+			}
+		}
+	};
 	const bool whole = a_vec && m0 + E <= p.M;   // one aligned 128-bit load per k
 	auto fetch = [&] (T (&dst)[E], uint32_t k)
 	{
@@ -314,33 +466,14 @@ skinny_cols_kernel (T* __restrict__ part, const T* __restrict__ A,
 #pragma unroll
 			for (int u = 0; u < UNROLL; ++u)
 			{
-				const T* brow = bs + (k + u) * NN;
-#pragma unroll
-				for (int n = 0; n < NN; ++n)
-				{
-					T bv = brow[n];
-#pragma unroll
-					for (int e = 0; e < E; ++e)
-					{
-						acc[e][n] = fma_t(a[u][e], bv, acc[e][n]);
-					}
-				}
+				multiply(a[u], bs + (k + u) * NN);
 			}
 		}
 		for (; k < len; ++k)
 		{
 			T a[E];
 			fetch(a, kc + k);
-			const T* brow = bs + k * NN;
-#pragma unroll
-			for (int n = 0; n < NN; ++n)
-			{
-#pragma unroll
-				for (int e = 0; e < E; ++e)
-				{
-					acc[e][n] = fma_t(a[e], brow[n], acc[e][n]);
-				}
-			}
+			multiply(a, bs + k * NN);
 		}
 	}
 #pragma unroll
@@ -352,7 +485,16 @@ skinny_cols_kernel (T* __restrict__ part, const T* __restrict__ A,
 #pragma unroll
 			for (int n = 0; n < NN; ++n)
 			{
-				dst[n] = acc[e][n];
+				if constexpr (F32)
+				{
+					float lo, hi;
+					unpack2(acc2[e / 2][n], lo, hi);
+					dst[n] = 0 == e % 2 ? lo : hi;
+				}
+				else
+				{
+					dst[n] = acc[e][n];
+				}
 			}
 		}
 	}
@@ -421,9 +563,10 @@ int skinny_launch (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A0,
 		int a_vec = (0 == ((uintptr_t) A & 15u) && 0 == p.a_rs % E) ? 1 : 0;
 		uint32_t kpad = (uint32_t) ((p.K + E - 1) / E * E);
 		// (up to 96 KB: two CTAs per SM still fit)
-		uint32_t kfit = (uint32_t) (96 * 1024 / (nn * sizeof(T)) - E) / (32 * E) * (32 * E);
+		uint32_t kfit = (uint32_t) (96 * 1024 / ((nn + 1) * sizeof(T))) / (32 * E) * (32 * E);
 		uint32_t kcap = std::min(kpad, std::max<uint32_t>(kfit, 32 * E));
-		size_t smem = (size_t) nn * (kcap + E) * sizeof(T);
+		// (kcap / E blocks of E x nn values + 16 bytes each, see skinny_block)
+		size_t smem = (size_t) (kcap / E) * (E * nn + E) * sizeof(T);
 		switch (nn)
 		{
 #define LLO_ROWS(NN) case NN:\
@@ -454,8 +597,16 @@ int skinny_launch (llo_cuda_ctx* ctx, const GemmParams& p0, T* C, const T* A0,
 		int a_vec = (0 == ((uintptr_t) A & 15u) && 0 == p.a_cs % E) ? 1 : 0;
 		uint64_t per_block = (uint64_t) SKINNY_COLS_THREADS * E;
 		uint32_t mblocks = (uint32_t) ((p.M + per_block - 1) / per_block);
+		// (four CTAs are resident per SM -- 118 registers x 128 threads; 6 per SM
+		// ran as 1.5 waves.  Measured, 1024x10x65536 with the fold pass, whose
+		// reads grow with the splits: 2 per SM 103 us, 3: 93, 4: 97, 6: 117, 8: 129)
+		uint32_t per_sm = 3;
+		if (const char* env = std::getenv("LLO_SKINNY_COLS_PER_SM"))
+		{
+			per_sm = (uint32_t) std::max(1, std::atoi(env)); // experiments only
+		}
 		uint32_t want = (uint32_t) std::max<uint64_t>(1,
-			((uint64_t) ctx->sm_count * 6 + mblocks - 1) / mblocks);
+			((uint64_t) ctx->sm_count * per_sm) / mblocks);
 		uint32_t k_per_block = (uint32_t) std::max<uint64_t>(64, (p.K + want - 1) / want);
 		uint32_t splits = (uint32_t) ((p.K + k_per_block - 1) / k_per_block);
 		if (splits > 65535)
