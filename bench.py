@@ -166,10 +166,26 @@ def cpu_chain(side, repeats):
 
 
 def cpu_worker(args):
-    """one of the `nproc` independent oracle processes of the all-core figure"""
+    """one of the `nproc` independent oracle processes of the all-core figures.
+    With --cpu-steps K (the reference arm): build the graph, warm up, print "ready", wait for
+    a line on stdin (all workers start their timed loop together), time K evaluations."""
     side = 1 << (args.cpu_log2n // 2)
-    sec, gbps = cpu_chain(side, max(1, args.cpu_repeats))
-    print(json.dumps({"sec": sec, "gbps": gbps}), flush=True)
+    if args.cpu_steps <= 0:
+        sec, gbps = cpu_chain(side, max(1, args.cpu_repeats))
+        print(json.dumps({"sec": sec, "gbps": gbps}), flush=True)
+        return
+    from cortenn_b200 import age, llo
+    oracle = oracle_module()
+    x, b = workloads.chain_inputs(side)
+    _, _, root = workloads.chain_graph(age, llo, x, b)
+    for _ in range(max(0, args.cpu_warmup)):
+        oracle.evaluate(root, F32)
+    print(json.dumps({"ready": 1}), flush=True)
+    sys.stdin.readline()
+    t0 = time.perf_counter()
+    for _ in range(args.cpu_steps):
+        oracle.evaluate(root, F32)
+    print(json.dumps({"sec": time.perf_counter() - t0, "steps": args.cpu_steps}), flush=True)
 
 
 def cpu_all_cores(args):
@@ -249,7 +265,40 @@ def cpu_side_baselines(age, llo):
     return out
 
 
+def reference_all_cores(args, side):
+    """`nproc` single-threaded oracle processes, each evaluating the chain sample args.steps
+    times after args.warmup warm-ups, started together: (seconds for the slowest, processes)"""
+    procs = os.cpu_count() or 1
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", "--cpu-log2n", str(args.ref_log2n),
+           "--cpu-steps", str(args.steps), "--cpu-warmup", str(args.warmup)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for key in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(key, None)
+    running = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                env=env, text=True) for _ in range(procs)]
+    try:
+        for p in running:
+            if "ready" not in json.loads(p.stdout.readline()):
+                raise RuntimeError("worker did not come up")
+        for p in running:
+            p.stdin.write("go\n")
+            p.stdin.flush()
+        secs = [json.loads(p.stdout.readline())["sec"] for p in running]
+        for p in running:
+            p.wait(timeout=60)
+        return max(secs), procs
+    except Exception:
+        for p in running:
+            p.kill()
+        return None, 0
+
+
 def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (the oracle port: the reference does
+    not build here) on the box's host cores.  The reference evaluator is
+    single-threaded (no threads, SIMD or BLAS: SURVEY.md 2.2), so "all the host threads it can
+    use" is one evaluation per core: `nproc` independent processes, like this repo's own
+    replicas of the chain at N > 1.  The single-thread figure rides along."""
     if rank != 0:
         return
     side = 1 << (args.ref_log2n // 2)
@@ -262,10 +311,21 @@ def run_reference(args, rank, world):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         oracle.evaluate(root, F32)
-    per_step = (time.perf_counter() - t0) / args.steps
-    value = workloads.chain_bytes(side) / per_step / 1e9
-    sample = ("the same chain on x=[%d,%d] (2^%d elements) per step; 1 thread: the reference "
-              "evaluator has no threads, SIMD or BLAS (SURVEY.md 2.2)" % (side, side, args.ref_log2n))
+    single_step = (time.perf_counter() - t0) / args.steps
+    single = workloads.chain_bytes(side) / single_step / 1e9
+    slowest, procs = (None, 0) if args.ref_single else reference_all_cores(args, side)
+    if slowest is None:
+        per_step, value, cores = single_step, single, 1
+        sample = ("the same chain on x=[%d,%d] (2^%d elements) per step; 1 thread: the reference "
+                  "evaluator has no threads, SIMD or BLAS (SURVEY.md 2.2)" % (side, side, args.ref_log2n))
+    else:
+        per_step = slowest / args.steps
+        value = procs * workloads.chain_bytes(side) / per_step / 1e9
+        cores = procs
+        sample = ("%d independent single-threaded evaluations (one process per core: the reference "
+                  "evaluator has no threads, SIMD or BLAS, SURVEY.md 2.2) of the same chain on "
+                  "x=[%d,%d] (2^%d elements) per step, started together, slowest process timed"
+                  % (procs, side, side, args.ref_log2n))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -273,8 +333,9 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "elementwise chain add(mul(exp(x),extend(b,1,{D})),permute(x,{1,0})), fp32, "
                                "bounded CPU sample of x=[16384,16384]", "sample_elements": side * side,
-                   "full_elements": 1 << args.log2n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+                   "full_elements": 1 << args.log2n, "processes": max(cores, 1)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "single_thread": {"value": single, "unit": UNIT, "ms_per_step": single_step * 1e3}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -900,6 +961,10 @@ def main():
     ap.add_argument("--skip-verify", action="store_true", help="do not compare the timed outputs with float64 numpy")
     ap.add_argument("--no-traffic-probe", action="store_true", help="do not run the ncu DRAM-bytes pass")
     ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-steps", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-warmup", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--ref-single", action="store_true",
+                    help="reference arm on one thread only (default: one evaluation per host core)")
     args = ap.parse_args()
     if args.cpu_worker:
         cpu_worker(args)
