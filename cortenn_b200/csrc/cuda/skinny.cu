@@ -12,9 +12,10 @@
 /// once, coalesced, stage the short one in shared memory, and sum in a fixed
 /// order (run-to-run deterministic; per-lane chains in ascending k, then a
 /// fixed shuffle tree / an ascending fold over k ranges).  Measured
-/// (tools/gemm_bench.py): 8192x10x1024 75 -> 30 us, 1024x10x8192 70 -> 54 us,
-/// 65536x10x1024 384 -> 176 us, 1024x10x65536 356 -> 292 us -- still
-/// latency-bound (1.0-1.5 TB/s).
+/// (tools/gemm_bench.py, tiled kernel -> round 1 -> round 2): 8192x10x1024
+/// 75 -> 30 -> 23 us, 1024x10x8192 70 -> 54 -> 37 us, 65536x10x1024
+/// 384 -> 176 -> 73 us (3.7 TB/s), 1024x10x65536 356 -> 292 -> 93 us with its
+/// fold -- what is left is global-load latency at 12-16 warps per SM.
 ///
 
 #include <algorithm>
@@ -108,12 +109,14 @@ __device__ __forceinline__ void halving_tree (T (&v)[C0], int lane, int& base, b
 }
 
 // ---- skinny output, A rows contiguous along k: a warp per R rows at a time -------
-// B is staged chunk by chunk (skinny_kc k's) in shared memory TRANSPOSED,
-// bs[n][k]: lane l multiplies the E = 16 / sizeof(T) consecutive k at
-// E (l + 32 i) of the chunk, so it reads 16 bytes of each of its A rows per
-// step (a warp: 512 contiguous bytes per row) and one LDS.128 per column of B
-// (consecutive lanes, consecutive 16 bytes: conflict-free).  Per-lane sums run
-// in ascending k; the 32 of them fold through a fixed xor-shuffle tree.
+// B is staged (whole when it fits, else chunk by chunk) in shared memory
+// k-major, bs[k / E][k % E][n] (skinny_block): lane l multiplies the
+// E = 16 / sizeof(T) consecutive k at E (l + 32 i) of the chunk, so it reads
+// 16 bytes of each of its A rows per step (a warp: 512 contiguous bytes per
+// row) and NN / E 128-bit vectors of B per k, each holding E neighbouring
+// columns (the 16-byte pad per block keeps the lanes of a quarter warp on
+// different bank groups).  Per-lane sums run in ascending k; the 32 of them
+// fold through a fixed xor tree (halving_tree).
 //
 // These are bandwidth problems and what decides them is BYTES IN FLIGHT
 // (round 1: 1.0-1.5 TB/s with 32 bytes per lane outstanding).  So a warp owns
@@ -121,6 +124,9 @@ __device__ __forceinline__ void halving_tree (T (&v)[C0], int lane, int& base, b
 // multiplied (128-192 bytes per lane, ~100 KB per SM), and the short dimension
 // is a template argument (NN = N rounded up to 4) so that padding columns cost
 // neither registers nor FMAs and two CTAs stay resident.
+// Then issue slots (ncu: 4047 warp instructions per 4 rows, 1536 of them FFMA):
+// column pairs share an FFMA2 (B staged k-major so that a row vector holds
+// neighbouring columns) and the 32 per-lane sums fold through a halving tree.
 
 // k's of B staged at a time: 512 (fp32) / 256 (fp64), <= 35 KB of shared memory
 template <typename T>

@@ -16,10 +16,12 @@
 ///      and rewrites them with the named llo::optimize passes,
 ///   2. evaluates all of them in ONE plan, every gradient written straight
 ///      into its slot of one packed device buffer (no pack copies),
-///   3. folds the buffer over the ranks -- in backward order, bucket by bucket
-///      on a second lane (llo_cuda_allreduce_async), so the last layers'
-///      gradients travel over NVLink while the earlier layers' backward GEMMs
-///      still run; or with one ordered fold (bit-identical on every rank).
+///   3. folds the buffer over the ranks -- bucket by bucket on a second lane
+///      (llo_cuda_allreduce_async), so a layer's gradients travel over NVLink
+///      while the other layers' weight-gradient GEMMs still run (see
+///      ShardedOptions::deep_first_ for the order); or with one ordered fold
+///      (bit-identical on every rank),
+///   4. from the second call on replays the whole step from one CUDA graph.
 ///
 
 #ifndef LLO_SHARDED_HPP
