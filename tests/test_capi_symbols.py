@@ -2,6 +2,10 @@
 declares (no compute calls without a GPU)."""
 import os
 import re
+import shutil
+import subprocess
+
+import pytest
 
 import util
 from util import capi
@@ -67,3 +71,21 @@ def test_nvrtc_stand_in_header_matches_the_real_one():
         body = re.search(r"enum\s*\{\s*(LLO_OP_BAD.*?)\}", text, flags=re.S).group(1)
         return [t.strip().split("=")[0].strip() for t in body.replace("\n", " ").split(",") if t.strip()]
     assert opcodes(stub) == opcodes(real)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """the boundary is a C ABI: include/llo_cuda.h compiles as C99 (-pedantic) and a C
+    program links against the library and reads its ABI version"""
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    root = util.ROOT
+    src = tmp_path / "abi.c"
+    src.write_text('#include "llo_cuda.h"\n'
+                   'int main(void) { return llo_cuda_abi_version() == LLO_CUDA_ABI_VERSION ? 0 : 1; }\n')
+    lib_dir = os.path.join(root, "cortenn_b200")
+    exe = str(tmp_path / "abi")
+    subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                    str(src), "-L", lib_dir, "-lllo_cuda", "-Wl,-rpath," + lib_dir, "-o", exe],
+                   check=True, capture_output=True, timeout=120)
+    assert subprocess.run([exe], timeout=60).returncode == 0
