@@ -16,12 +16,13 @@ F4, F8, I4 = np.float32, np.float64, np.int32
 
 
 def functors(root):
-    seen, todo, n = set(), [root], 0
+    # (wrappers are kept alive while walking: a freed wrapper's id() may be handed to the next)
+    seen, todo, n = {}, [root], 0
     while todo:
         t = todo.pop()
         if id(t) in seen:
             continue
-        seen.add(id(t))
+        seen[id(t)] = t
         kids = t.children()
         if t.opname():
             n += 1
