@@ -99,3 +99,27 @@ def test_optimize_is_idempotent(data):
     (twice,), second = llo.optimize([once], llo.OPT_EXACT)
     assert second["functors_after"] == second["functors_before"] == first["functors_after"]
     assert count(twice) == count(once)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.data())
+def test_random_graphs_survive_pbm_save_and_load(data):
+    """pbm::GraphSaver -> bytes -> pbm::load_graph (pbm/src/save.cpp, load.cpp): the loaded
+    graph -- rewritten or as derived -- evaluates to the same bits and saves to the same bytes"""
+    pool = leaves()
+    root = build(data.draw, pool, data.draw(st.integers(1, 4)))
+    roots = [root, llo.derive(root, pool[1])] if root.opname() else [root]
+    if data.draw(st.booleans()):
+        roots = list(llo.optimize(roots, llo.OPT_EXACT)[0])
+    blob = llo.save_graph(roots)
+    loaded = llo.load_graph(blob)
+    assert len(loaded["roots"]) >= 1
+    # roots that are sub-graphs of other roots are not roots of the file: compare by value
+    want = {oracle.evaluate(r, np.dtype(np.float64)).tobytes() for r in roots}
+    got = {oracle.evaluate(r, np.dtype(np.float64)).tobytes() for r in loaded["roots"]}
+    assert got <= want and len(got) >= 1
+    # one round trip is a fixed point of the byte form
+    blob2 = llo.save_graph(loaded["roots"])
+    again = llo.load_graph(blob2)
+    assert len(again["nodes"]) == len(loaded["nodes"])
+    assert llo.save_graph(again["roots"]) == blob2
