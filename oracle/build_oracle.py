@@ -4,7 +4,7 @@ box):  liboracle.so (C entry points, host pointers)  and  _oracle.*.so (pybind).
 
 /root/reference cannot be compiled here (it needs bazel, the un-vendored
 Tenncor@959d51e sources and gtest), so there is no oracle/_ref: the oracle is a
-port, pinned by the reference's golden vectors (tests/test_oracle_golden.py).
+port, pinned by the reference's golden vectors (tests/test_golden.py, tests/test_pbm.py, tests/test_shear_cpp.py).
 """
 import os
 import subprocess
